@@ -1,0 +1,196 @@
+/*
+ * vpe.h — C-ABI of the B200-native sparse volumetric particle engine.
+ *
+ * Drop-in boundary for ONE hot path of rajabala/Volumetric-Particles-For-Unity:
+ *   Fill Volume  (BinParticlesToMetavoxels + FillMetavoxels + FillVolume.shader)
+ *   Ray March    (RenderMetavoxels + RayMarchVoxel.shader)
+ *
+ * The reference has no FFI boundary of its own: the path sits behind Unity's managed
+ * graphics API (Graphics.Blit / DrawMeshNow / Material.Set*).  Each entry point below cites
+ * the reference interface it replaces.  Citations are relative to /root/reference:
+ *   VPR.cs       = Assets/Main Scene/VolumetricParticleRenderer.cs
+ *   Fill.shader  = Assets/Shaders/Metavoxel/FillVolume.shader
+ *   March.shader = Assets/Shaders/Metavoxel/RayMarchVoxel.shader
+ *
+ * Two libraries export exactly these symbols:
+ *   libvpe_cuda.so  — the product: hand-written sm_100a CUDA kernels (no CPU fallback).
+ *   libvpe_ref.so   — the CPU oracle under oracle/ (test infrastructure only).
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every call returns VPE_OK (0) or a negative
+ *     VPE_E_* code; the message is available from vpe_last_error().
+ *   - the caller owns every pointer it passes; inputs are consumed before the call returns;
+ *     outputs are caller-allocated.  "_device" variants take CUDA device pointers.
+ *   - a context is not thread-safe (the reference runs on Unity's main thread only).
+ *   - Unity conventions: left-handed world, +Z forward, quaternions (x,y,z,w), column vectors.
+ */
+#ifndef VPE_H_
+#define VPE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPE_ABI_VERSION 1
+
+enum {
+    VPE_OK = 0,
+    VPE_E_INVALID_ARG = -1,   /* NULL pointer, bad dimension, border out of range ...      */
+    VPE_E_NOT_READY = -2,     /* march before fill, missing cubemap ...                    */
+    VPE_E_CUDA = -3,          /* a CUDA runtime call or kernel failed                      */
+    VPE_E_OUT_OF_MEMORY = -4, /* brick pool does not fit                                   */
+    VPE_E_UNSUPPORTED = -5    /* entry point not available in this library                 */
+};
+
+enum { VPE_BIN_REFERENCE = 0, /* bug-compatible candidate range, VPR.cs:425-438           */
+       VPE_BIN_EXACT = 1      /* test every cell the enlarged box can reach               */ };
+
+/* Unity Transform.{position,rotation} (VPR.cs:136,188-192,380,418,616). Scale is 1. */
+typedef struct VpeTransform {
+    float position[3];
+    float rotation[4]; /* quaternion x,y,z,w */
+} VpeTransform;
+
+/* Public inspector fields of VolumetricParticleRenderer, VPR.cs:82-101, plus the constants the
+ * reference hard-codes for its light camera (VPR.cs:342,365). */
+typedef struct VpeConfig {
+    int32_t numMetavoxelsX, numMetavoxelsY, numMetavoxelsZ; /* VPR.cs:82                     */
+    float mvScale;                    /* VPR.cs:83 — cubic metavoxels only (VPR.cs:422,425)  */
+    int32_t numVoxelsInMetavoxel;     /* VPR.cs:84  (any N >= 2; the shader's 32 cap lifted) */
+    int32_t numBorderVoxels;          /* VPR.cs:85  0 <= b <= (N-2)/2                        */
+    int32_t rayMarchSteps;            /* VPR.cs:89  steps per metavoxel                      */
+    float ambientColor[3];            /* VPR.cs:90                                           */
+    float displacementScale;          /* VPR.cs:94                                           */
+    int32_t fadeOutParticles;         /* VPR.cs:95                                           */
+    float opacityFactor;              /* VPR.cs:100                                          */
+    int32_t softParticleStepDistance; /* VPR.cs:101                                          */
+    float lightNear, lightFar;        /* VPR.cs:342 (0.3, 1000)                              */
+    float lightCameraDistance;        /* VPR.cs:365 (200)                                    */
+    int32_t binMode;                  /* VPE_BIN_*                                           */
+    float marchEarlyOutTransmittance; /* 0 = exact reference semantics (default); > 0 lets the
+                                         CUDA march stop a ray once 1-alpha falls below it   */
+    int32_t slabZBegin, slabZEnd;     /* light-axis slab [begin,end) owned by this context;
+                                         0,0 = whole grid (single GPU)                       */
+} VpeConfig;
+
+/* The ParticleSystem.Particle fields the reference reads (VPR.cs:418,425,583-586). 28 bytes. */
+typedef struct VpeParticle {
+    float position[3]; /* emitter-local                           */
+    float size;        /* diameter, world units                   */
+    float rotationDeg; /* about the emitter's forward axis        */
+    float lifetime;    /* remaining                               */
+    float startLifetime;
+} VpeParticle;
+
+/* Camera.main.{transform, fieldOfView}, Screen.{width,height} (VPR.cs:616,642,733-737,778). */
+typedef struct VpeCamera {
+    VpeTransform transform;
+    float fovYDegrees;
+    int32_t width, height;
+} VpeCamera;
+
+typedef struct VpeStats {
+    int32_t numParticles;        /* VPR.cs:124                                              */
+    int32_t numMetavoxelsCovered;/* VPR.cs:125 (in this context's slab)                     */
+    int64_t numParticlePairs;    /* sum of list lengths after binning                       */
+    int64_t voxelsFilled;        /* numMetavoxelsCovered * N^3                              */
+    int64_t raySamples;          /* iterations of March.shader:254-279 in the last march    */
+    int32_t zBoundary;           /* VPR.cs:648 of the last march                            */
+    int32_t fillLaunches;        /* kernels launched by the last fill (0 in the oracle)     */
+    int32_t marchLaunches;       /* kernels launched by the last march                      */
+    float fillMs, marchMs;       /* device time of the last fill / march (CUDA events);
+                                    wall time in the oracle                                 */
+    int64_t brickPoolBytes;
+} VpeStats;
+
+typedef struct VpeContext VpeContext;
+
+/* Defaults = the demo scene's inspector values (Assets/Volumetric_Particle_System.unity:9013-9026). */
+void vpe_default_config(VpeConfig* cfg);
+
+/* ≙ Start()/CreateResources()/CreateMetavoxelGrid(), VPR.cs:132-149,224-317.
+ * device: CUDA ordinal (ignored by the oracle). */
+int vpe_create(const VpeConfig* cfg, int device, VpeContext** out);
+int vpe_destroy(VpeContext* ctx);
+
+/* ≙ the GUI setters VPR.cs:1040-1119. Grid dims / N / slab may not change after create. */
+int vpe_set_config(VpeContext* ctx, const VpeConfig* cfg);
+
+/* ≙ UpdateMetavoxelPositions + UpdatePositionOfCameraAtLight, VPR.cs:361-394;
+ * light = dirLight.transform, gridCenter = gridCenter.transform.position. */
+int vpe_set_light(VpeContext* ctx, const VpeTransform* light, const float gridCenter[3]);
+
+/* ≙ Material "_DisplacementTexture" (Fill.shader:57,116): 6 faces x edge x edge, R channel,
+ * faces in Unity order +X,-X,+Y,-Y,+Z,-Z. */
+int vpe_set_displacement_cubemap(VpeContext* ctx, const uint8_t* r8, int edge);
+
+/* ≙ lightDepthMap (VPR.cs:274, Fill.shader:59,216): (NY*N) rows x (NX*N) floats in [0,1];
+ * NULL = no occluders (all 1.0). */
+int vpe_set_light_depth_map(VpeContext* ctx, const float* depth01);
+
+/* ≙ BinParticlesToMetavoxels + FillMetavoxels, VPR.cs:397-520 (+ FillVolume.shader).
+ * emitter = particleSys.transform. */
+int vpe_fill(VpeContext* ctx, const VpeParticle* particles, int n, const VpeTransform* emitter);
+
+/* ≙ RenderMetavoxels, VPR.cs:637-713 (+ RayMarchVoxel.shader).
+ * rgba: height*width*4 floats, premultiplied RGB + coverage alpha (≙ particlesRT, VPR.cs:228,
+ * as float4, no 8-bit quantisation); row 0 is screen-space y = 0 of March.shader:189.
+ * samples: optional height*width int32 = loop iterations per pixel (≙ _ShowNumSamples). */
+int vpe_march(VpeContext* ctx, const VpeCamera* cam, float* rgba, int32_t* samples);
+
+/* Same, for a list of pixel indices (y*width + x); rgba is n*4, samples n. Used for parity at
+ * sizes where the scalar oracle cannot render the full image. */
+int vpe_march_pixels(VpeContext* ctx, const VpeCamera* cam, const int32_t* pixels, int n,
+                     float* rgba, int32_t* samples);
+
+/* ---- device-resident variants (CUDA library only; the oracle returns VPE_E_UNSUPPORTED) ---- */
+int vpe_set_stream(VpeContext* ctx, void* cudaStream);
+int vpe_fill_device(VpeContext* ctx, const VpeParticle* particles_dev, int n,
+                    const VpeTransform* emitter);
+int vpe_march_device(VpeContext* ctx, const VpeCamera* cam, float* rgba_dev, int32_t* samples_dev);
+
+/* ---- multi-GPU light-axis slabs ----
+ * vpe_fill_prepare bins the particles into this context's slab and sizes the brick pool;
+ * vpe_fill_region sweeps the metavoxel columns [x0,x1) x [y0,y1) through the slab's z-slices,
+ * reading and updating the context's light sheet; the caller moves sheet tiles between slabs
+ * (NCCL send/recv on the pointer returned by vpe_light_sheet_device). vpe_fill == prepare +
+ * region(whole grid). */
+int vpe_fill_prepare(VpeContext* ctx, const VpeParticle* particles, int n,
+                     const VpeTransform* emitter, int particlesOnDevice);
+int vpe_fill_region(VpeContext* ctx, int x0, int x1, int y0, int y1);
+float* vpe_light_sheet_device(VpeContext* ctx);
+/* Slab-local march: two premultiplied RGBA partial images (device, height*width*4 floats each):
+ * over = the slab's slices <= zBoundary composited back-to-front (phase 1, VPR.cs:652-681),
+ * under = its slices > zBoundary composited front-to-back (phase 2, VPR.cs:688-711). */
+int vpe_march_partial_device(VpeContext* ctx, const VpeCamera* cam, float* over_dev,
+                             float* under_dev, int32_t* samples_dev);
+/* Composite R slabs' partial images for a pixel range in reference order (phase 1 slabs in
+ * ascending z with OVER, then phase 2 slabs in ascending z with UNDER). parts_dev[2*r+0] = over,
+ * parts_dev[2*r+1] = under of slab r (device pointers, numPixels*4 floats each). */
+int vpe_composite_device(VpeContext* ctx, const float* const* parts_dev, int numSlabs,
+                         int numPixels, float* rgba_dev);
+
+/* ---- test hooks ---- */
+/* brick (x,y,z) as N*N*N half4 in [slice][row][col] order (≙ mvFillTextures[z,y,x], VPR.cs:312);
+ * returns 1 in *covered if the metavoxel has particles (VPR.cs:511), else 0 and no data. */
+int vpe_read_brick(VpeContext* ctx, int x, int y, int z, uint16_t* half4, int* covered);
+/* light sheet (≙ lightPropogationUAV, VPR.cs:266): (NY*N) rows x (NX*N) floats. */
+int vpe_read_light_sheet(VpeContext* ctx, float* sheet);
+/* particle indices binned to metavoxel (x,y,z), in list order; returns count in *n (cap = size
+ * of idx). ≙ mvGrid[z,y,x].mParticlesCovered, VPR.cs:453. */
+int vpe_read_particle_list(VpeContext* ctx, int x, int y, int z, int32_t* idx, int cap, int* n);
+/* world-space centre of metavoxel (x,y,z) ≙ mvGrid[z,y,x].mPos, VPR.cs:390. */
+int vpe_read_metavoxel_position(VpeContext* ctx, int x, int y, int z, float pos[3]);
+
+int vpe_get_stats(VpeContext* ctx, VpeStats* stats);
+const char* vpe_last_error(VpeContext* ctx);
+int vpe_abi_version(void);
+/* "cuda" or "oracle" */
+const char* vpe_backend(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPE_H_ */

@@ -1,0 +1,689 @@
+// vpe_cuda.cu — libvpe_cuda.so: the C-ABI of include/vpe.h over hand-written sm_100a kernels.
+//
+// Host orchestration mirrors the per-frame loop of VolumetricParticleRenderer (VPR.cs:181-220):
+//   vpe_fill   ≙ BinParticlesToMetavoxels + FillMetavoxels   (VPR.cs:397-520)
+//   vpe_march  ≙ RenderMetavoxels                            (VPR.cs:637-713)
+// but instead of one draw call per metavoxel it issues a handful of launches: particle set-up and
+// counting-sort binning, then one fill launch per light-axis slice (the only true dependency), then
+// one march launch for the whole image that walks the metavoxels per ray in the reference's
+// submission order.  There is NO CPU fallback: every entry point that computes runs on the GPU.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/vpe.h"
+#include "vpe_kernels.cuh"
+
+using namespace vpe;
+
+#define CUDA_TRY(ctx, expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t e_ = (expr);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            char buf_[512];                                                                          \
+            snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            (ctx)->err = buf_;                                                                       \
+            return e_ == cudaErrorMemoryAllocation ? VPE_E_OUT_OF_MEMORY : VPE_E_CUDA;               \
+        }                                                                                            \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct VpeContext {
+    VpeConfig cfg;
+    std::string err;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    // state
+    VpeTransform light;
+    float center[3] = {0, 0, 0};
+    bool lightSet = false, cubeSet = false, prepared = false, filledOnce = false;
+    GridParams g;
+    M3 lightRot;
+    F3 lightFwdRaw;
+    // device buffers
+    DevBuf<float> dParticles;        // n*7 staging for host particle input
+    DevBuf<ParticleFill> dPfill;
+    DevBuf<ParticleBin> dPbin;
+    DevBuf<int> dCellCount, dCellStart, dBrickOf, dCovered, dSliceStart, dPairs, dTotals;
+    DevBuf<int2> dBlockSums;
+    DevBuf<float> dCube, dDepth, dSheet;
+    DevBuf<uint2> dBricks;
+    DevBuf<float4> dMvCam;
+    DevBuf<int> dRank, dPixels, dSamples;
+    DevBuf<float4> dImage, dImage2;
+    DevBuf<unsigned long long> dTotalSamples;
+    DevBuf<const float4*> dParts;
+    bool depthSet = false;
+    int cubeEdge = 0;
+    // pinned host staging
+    int* hCounts = nullptr;  // [NZ + 3]: sliceStart[NZ+1], totals[2]
+    unsigned long long* hTotalSamples = nullptr;
+    std::vector<int> sliceStart;
+    int nParticles = 0, nCovered = 0, nPairs = 0;
+    int numCells = 0;
+    // timing
+    cudaEvent_t evFill0 = nullptr, evFill1 = nullptr, evMarch0 = nullptr, evMarch1 = nullptr;
+    bool fillTimed = false, marchTimed = false;
+    VpeStats stats;
+};
+
+namespace {
+
+int fail(VpeContext* c, int code, const char* msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+int validate_config(const VpeConfig& c, std::string& why) {
+    if (c.numMetavoxelsX < 1 || c.numMetavoxelsY < 1 || c.numMetavoxelsZ < 1) { why = "grid dims must be >= 1"; return -1; }
+    if ((long long)c.numMetavoxelsX * c.numMetavoxelsY * c.numMetavoxelsZ > (1ll << 26)) { why = "grid too large"; return -1; }
+    if (c.numVoxelsInMetavoxel < 2 || c.numVoxelsInMetavoxel > 256) { why = "numVoxelsInMetavoxel must be in [2,256]"; return -1; }
+    // fill clamps the border to [0,N-2] (VPR.cs:528), the march does not (VPR.cs:726)
+    if (c.numBorderVoxels < 0 || c.numBorderVoxels > (c.numVoxelsInMetavoxel - 2) / 2) { why = "numBorderVoxels out of range"; return -1; }
+    if (!(c.mvScale > 0.0f)) { why = "mvScale must be > 0"; return -1; }
+    if (c.rayMarchSteps < 1) { why = "rayMarchSteps must be >= 1"; return -1; }
+    if (c.slabZBegin < 0 || c.slabZEnd > c.numMetavoxelsZ || c.slabZBegin >= c.slabZEnd) { why = "bad slab range"; return -1; }
+    return 0;
+}
+
+void normalise_slab(VpeConfig& c) {
+    if (c.slabZBegin == 0 && c.slabZEnd == 0) c.slabZEnd = c.numMetavoxelsZ;
+}
+
+F3 forward_of(const M3& r) { return f3(r.m[0][2], r.m[1][2], r.m[2][2]); }
+
+// Everything the kernels need that depends only on config + light (VPR.cs:139, 361-394, 523-554).
+void rebuild_grid_params(VpeContext* c) {
+    GridParams& g = c->g;
+    const VpeConfig& k = c->cfg;
+    memset(&g, 0, sizeof(g));
+    g.NX = k.numMetavoxelsX; g.NY = k.numMetavoxelsY; g.NZ = k.numMetavoxelsZ;
+    g.N = k.numVoxelsInMetavoxel;
+    g.border = std::min(std::max(k.numBorderVoxels, 0), g.N - 2);  // VPR.cs:528
+    g.z0 = k.slabZBegin; g.z1 = k.slabZEnd;
+    g.binMode = k.binMode;
+    g.s = k.mvScale;
+    g.sb = k.mvScale * (float)g.N / (float)(g.N - 2 * k.numBorderVoxels);  // VPR.cs:139
+    g.Nf = (float)g.N;
+    g.center = f3(c->center[0], c->center[1], c->center[2]);
+    c->lightRot = quat_to_m3(c->light.rotation);
+    g.L2W = trs(f3(c->light.position[0], c->light.position[1], c->light.position[2]), c->lightRot, 1.0f);
+    g.W2L = affine_inverse(g.L2W);
+    g.lsCenter = xform_point(g.W2L, g.center);  // VPR.cs:380
+    c->lightFwdRaw = forward_of(c->lightRot);
+    {
+        // Vector3.normalized (VPR.cs:535)
+        float mag = sqrtf(dot3(c->lightFwdRaw, c->lightFwdRaw));
+        g.lightFwd = mag > 1e-5f ? f3(c->lightFwdRaw.x / mag, c->lightFwdRaw.y / mag, c->lightFwdRaw.z / mag) : f3(0, 0, 0);
+    }
+    g.Ab = trs(f3(0, 0, 0), c->lightRot, g.sb);
+    g.Lb = affine_inverse_linear(g.Ab);
+    g.As = trs(f3(0, 0, 0), c->lightRot, g.s);
+    g.Ls = affine_inverse_linear(g.As);
+    {
+        // lightCamera.transform: position = centre - forward * 200, the light's rotation (VPR.cs:365-366)
+        F3 lc = f3(g.center.x - c->lightFwdRaw.x * k.lightCameraDistance, g.center.y - c->lightFwdRaw.y * k.lightCameraDistance,
+                   g.center.z - c->lightFwdRaw.z * k.lightCameraDistance);
+        Affine w2lc = affine_inverse(trs(lc, c->lightRot, 1.0f));
+        for (int j = 0; j < 4; j++) g.w2lcRow2[j] = w2lc.m[2][j];
+    }
+    g.oneVoxelSize = g.sb / g.Nf;  // Fill.shader:160
+    g.lightStep = f3(g.lightFwd.x * g.oneVoxelSize, g.lightFwd.y * g.oneVoxelSize, g.lightFwd.z * g.oneVoxelSize);
+    for (int i = 0; i < 3; i++) g.ambient[i] = k.ambientColor[i];
+    g.ds = k.displacementScale;
+    g.opacityFactor = k.opacityFactor;
+    g.fade = k.fadeOutParticles;
+    {
+        float a = 1.0f / (k.lightFar - k.lightNear);  // Fill.shader:217
+        g.depthB = -k.lightNear * a;
+        g.depthRcpA = 1.0f / a;
+    }
+    g.cubeEdge = c->cubeEdge;
+}
+
+int sync_stream(VpeContext* c) {
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return VPE_OK;
+}
+
+inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- fill -------------------------------------------------------------------------------------
+int fill_prepare_impl(VpeContext* c, const float* particlesDev, int n, const VpeTransform* em) {
+    GridParams& g = c->g;
+    const int cells = c->numCells;
+    CUDA_TRY(c, cudaEventRecord(c->evFill0, c->stream));
+    c->fillTimed = false;
+    c->stats.fillLaunches = 0;
+    CUDA_TRY(c, c->dPfill.ensure(std::max(n, 1)));
+    CUDA_TRY(c, c->dPbin.ensure(std::max(n, 1)));
+    CUDA_TRY(c, cudaMemsetAsync(c->dCellCount.p, 0, sizeof(int) * cells, c->stream));
+    EmitterParams ep;
+    M3 er = quat_to_m3(em->rotation);
+    ep.E2W = trs(f3(em->position[0], em->position[1], em->position[2]), er, 1.0f);
+    ep.forward = forward_of(er);
+    if (n > 0) {
+        k_particle_setup<<<div_up(n, 128), 128, 0, c->stream>>>(g, ep, particlesDev, n, c->dPfill.p, c->dPbin.p, c->dCellCount.p);
+        c->stats.fillLaunches++;
+    }
+    const int nb = div_up(cells, SCAN_BLOCK);
+    k_scan_reduce<<<nb, SCAN_BLOCK, 0, c->stream>>>(c->dCellCount.p, cells, c->dBlockSums.p);
+    k_scan_blocks<<<1, SCAN_BLOCK, 0, c->stream>>>(c->dBlockSums.p, nb, c->dTotals.p);
+    k_scan_final<<<nb, SCAN_BLOCK, 0, c->stream>>>(c->dCellCount.p, cells, g.NX * g.NY, g.NZ, c->dBlockSums.p, c->dTotals.p,
+                                                  c->dCellStart.p, c->dBrickOf.p, c->dCovered.p, c->dSliceStart.p);
+    c->stats.fillLaunches += 3;
+    // the host needs the covered count (brick pool size) and the per-slice counts (launch grids)
+    CUDA_TRY(c, cudaMemcpyAsync(c->hCounts, c->dSliceStart.p, sizeof(int) * (g.NZ + 1), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->hCounts + g.NZ + 1, c->dTotals.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->sliceStart.assign(c->hCounts, c->hCounts + g.NZ + 1);
+    c->nPairs = c->hCounts[g.NZ + 1];
+    c->nCovered = c->hCounts[g.NZ + 2];
+    c->nParticles = n;
+    CUDA_TRY(c, c->dPairs.ensure(std::max(c->nPairs, 1)));
+    if (n > 0 && c->nPairs > 0) {
+        k_scatter_pairs<<<div_up(n, 128), 128, 0, c->stream>>>(g, c->dPbin.p, n, c->dCellCount.p, c->dCellStart.p, c->dPairs.p);
+        k_sort_lists<<<div_up(c->nCovered, 128), 128, 0, c->stream>>>(c->dCovered.p, c->dTotals.p + 1, c->dCellStart.p, c->dPairs.p);
+        c->stats.fillLaunches += 2;
+    }
+    // brick pool: one N^3 half4 brick per covered metavoxel (≙ lazily created mvFillTextures, VPR.cs:565-566)
+    const size_t brickTexels = (size_t)g.N * g.N * g.N;
+    size_t want = (size_t)c->nCovered;
+    if (want * brickTexels > c->dBricks.cap) {
+        size_t padded = std::min((size_t)cells, want + want / 16 + 8);
+        cudaError_t e = c->dBricks.ensure(padded * brickTexels);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = c->dBricks.ensure(want * brickTexels);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(c, VPE_E_OUT_OF_MEMORY, "brick pool does not fit in device memory");
+        }
+    }
+    // VPR.cs:498-499: clear the light propagation texture to 1
+    const size_t sheetN = (size_t)g.NX * g.N * g.NY * g.N;
+    k_fill_value<<<std::min(div_up(sheetN, 256), 148 * 8), 256, 0, c->stream>>>(c->dSheet.p, sheetN, 1.0f);
+    c->stats.fillLaunches++;
+    CUDA_TRY(c, cudaGetLastError());
+    c->prepared = true;
+    c->stats.numParticles = n;
+    c->stats.numMetavoxelsCovered = c->nCovered;
+    c->stats.numParticlePairs = c->nPairs;
+    c->stats.voxelsFilled = (int64_t)c->nCovered * (int64_t)brickTexels;
+    return VPE_OK;
+}
+
+int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1) {
+    GridParams& g = c->g;
+    FillArgs a;
+    a.covered = c->dCovered.p; a.sliceStart = c->dSliceStart.p; a.cellStart = c->dCellStart.p; a.pairs = c->dPairs.p;
+    a.pfill = c->dPfill.p; a.cube = c->dCube.p; a.depth = c->depthSet ? c->dDepth.p : nullptr;
+    a.sheet = c->dSheet.p; a.bricks = c->dBricks.p;
+    a.x0 = x0; a.x1 = x1; a.y0 = y0; a.y1 = y1;
+    const int tiles = div_up((long long)g.N * g.N, FILL_THREADS);
+    for (int zz = g.z0; zz < g.z1; zz++) {  // nearest the light first (VPR.cs:505)
+        int count = c->sliceStart[zz + 1] - c->sliceStart[zz];
+        if (count <= 0) continue;           // VPR.cs:511
+        k_fill_slice<<<dim3(count, tiles), FILL_THREADS, 0, c->stream>>>(g, a, zz);
+        c->stats.fillLaunches++;
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaEventRecord(c->evFill1, c->stream));
+    c->fillTimed = true;
+    c->filledOnce = true;
+    return VPE_OK;
+}
+
+// ---- march ------------------------------------------------------------------------------------
+struct SortData {  // ≙ MetavoxelSortData, VPR.cs:43-62
+    int x, y;
+    float distance;
+};
+
+int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nPixels, float4* rgbaDev, float4* underDev,
+               int* samplesDev, bool partial) {
+    GridParams& g = c->g;
+    const VpeConfig& k = c->cfg;
+    if (cam->width < 1 || cam->height < 1) return fail(c, VPE_E_INVALID_ARG, "bad image size");
+    MarchParams m;
+    memset(&m, 0, sizeof(m));
+    m.W = cam->width; m.H = cam->height;
+    m.Wf = (float)cam->width; m.Hf = (float)cam->height;
+    m.aspect = m.Wf / m.Hf;                                                   // March.shader:190
+    {
+        float fovRad = 0.0174532924f * cam->fovYDegrees;                      // VPR.cs:734
+        float tanHalf = (float)tan((double)(fovRad / 2.0f));                  // March.shader:193
+        m.negRcpTan = -(1.0f / tanHalf);
+    }
+    F3 camPos = f3(cam->transform.position[0], cam->transform.position[1], cam->transform.position[2]);
+    M3 camRot = quat_to_m3(cam->transform.rotation);
+    Affine camL2W = trs(camPos, camRot, 1.0f);
+    Affine C2W = camL2W;  // cameraToWorldMatrix: OpenGL convention, -Z forward
+    for (int i = 0; i < 3; i++) C2W.m[i][2] = -C2W.m[i][2];
+    Affine W2C = affine_inverse(camL2W);  // worldToCameraMatrix
+    for (int j = 0; j < 4; j++) W2C.m[2][j] = -W2C.m[2][j];
+    const float maxGridDim = (float)std::max(g.NX, std::max(g.NY, g.NZ));     // March.shader:207-208
+    {
+        float csVolOriginZ = ((W2C.m[2][0] * g.center.x + W2C.m[2][1] * g.center.y) + W2C.m[2][2] * g.center.z) + W2C.m[2][3];  // :206
+        float csVolHalfZ = 1.73205f * 0.5f * maxGridDim * g.s;                // :210
+        m.csZVolMin = csVolOriginZ + csVolHalfZ;                              // :211
+        float csRayLength = 2.0f * csVolHalfZ;                                // :214
+        float total = maxGridDim * (float)k.rayMarchSteps;                    // :221
+        float oneOver = 1.0f / total;                                         // :222
+        float mvRayLength = csRayLength * (1.0f / g.s);                       // :223
+        m.stepSize = mvRayLength * oneOver;                                   // :224
+    }
+    m.borderVoxelOffset = (1.0f / g.Nf) * (float)k.numBorderVoxels;           // :245
+    m.sampleScale = 1.0f - 2.0f * m.borderVoxelOffset;                        // :258
+    m.softDistance = k.softParticleStepDistance;
+    m.softRcp = 1.0f / (float)k.softParticleStepDistance;                     // :269
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++)
+            m.C2Mlin[i][j] = (g.Ls.b[i][0] * C2W.m[0][j] + g.Ls.b[i][1] * C2W.m[1][j]) + g.Ls.b[i][2] * C2W.m[2][j];  // VPR.cs:778
+        m.c2wT[i] = C2W.m[i][3];
+    }
+    // VPR.cs:613-632 SortMetavoxelSlicesFarToNearFromEye: keys from slice 0; ties by (y,x)
+    std::vector<SortData> asc;
+    asc.reserve((size_t)g.NX * g.NY);
+    for (int yy = 0; yy < g.NY; yy++)
+        for (int xx = 0; xx < g.NX; xx++) {
+            F3 d = sub(mv_center(g, xx, yy, 0), camPos);
+            asc.push_back(SortData{xx, yy, dot3(d, d)});
+        }
+    std::stable_sort(asc.begin(), asc.end(), [](const SortData& a, const SortData& b) { return a.distance < b.distance; });
+    std::vector<int> rank((size_t)g.NX * g.NY);
+    for (size_t i = 0; i < asc.size(); i++) rank[(size_t)asc[i].y * g.NX + asc[i].x] = (int)i;
+    // VPR.cs:642-648
+    {
+        F3 lsCam = xform_point(g.W2L, camPos);
+        float lsFirst = xform_point(g.W2L, mv_center(g, 0, 0, 0)).z;
+        float blendOverIndex = (lsCam.z - lsFirst) / g.s;
+        int zB = (int)nearbyint((double)blendOverIndex);  // Mathf.RoundToInt
+        m.zBoundary = std::min(std::max(zB, -1), g.NZ - 1);
+    }
+    m.zOverBegin = std::max(0, g.z0);
+    m.zOverEnd = std::max(m.zOverBegin, std::min(m.zBoundary + 1, g.z1));
+    m.zUnderBegin = std::max(m.zBoundary + 1, g.z0);
+    m.zUnderEnd = std::max(m.zUnderBegin, g.z1);
+    m.earlyOut = k.marchEarlyOutTransmittance;
+    m.numPixels = pixelsDev ? nPixels : cam->width * cam->height;
+    m.maxSamplesPerMv = (int)(1.7320508f / m.stepSize) + 2;
+    m.wrap = k.numBorderVoxels == 0 ? 1 : 0;
+
+    CUDA_TRY(c, cudaEventRecord(c->evMarch0, c->stream));
+    c->marchTimed = false;
+    CUDA_TRY(c, cudaMemcpyAsync(c->dRank.p, rank.data(), sizeof(int) * rank.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->dTotalSamples.p, 0, sizeof(unsigned long long), c->stream));
+    k_mv_camera<<<div_up(c->numCells, 256), 256, 0, c->stream>>>(g, m, c->dBrickOf.p, c->dMvCam.p);
+    MarchArgs a;
+    a.mvCam = c->dMvCam.p; a.rankAsc = c->dRank.p; a.bricks = c->dBricks.p; a.pixels = pixelsDev;
+    a.rgba = rgbaDev; a.under = underDev; a.samples = samplesDev; a.totalSamples = c->dTotalSamples.p;
+    dim3 grid, block(128);
+    if (pixelsDev) grid = dim3(div_up(nPixels, 128));
+    else grid = dim3(div_up(cam->width, 16), div_up(cam->height, 8));
+    if (m.numPixels > 0) {
+        if (partial) k_march<true><<<grid, block, 0, c->stream>>>(g, m, a);
+        else k_march<false><<<grid, block, 0, c->stream>>>(g, m, a);
+    }
+    c->stats.marchLaunches = 2;
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(c->hTotalSamples, c->dTotalSamples.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaEventRecord(c->evMarch1, c->stream));
+    c->marchTimed = true;
+    c->stats.zBoundary = m.zBoundary;
+    return VPE_OK;
+}
+
+int check_ready_for_march(VpeContext* c) {
+    if (!c->lightSet) return fail(c, VPE_E_NOT_READY, "vpe_set_light has not been called");
+    if (!c->filledOnce) return fail(c, VPE_E_NOT_READY, "vpe_fill has not been called");
+    return VPE_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+void vpe_default_config(VpeConfig* cfg) {
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->numMetavoxelsX = cfg->numMetavoxelsY = cfg->numMetavoxelsZ = 10;
+    cfg->mvScale = 3.0f;
+    cfg->numVoxelsInMetavoxel = 32;
+    cfg->numBorderVoxels = 1;
+    cfg->rayMarchSteps = 64;
+    cfg->ambientColor[0] = cfg->ambientColor[1] = cfg->ambientColor[2] = 0.2f;
+    cfg->displacementScale = 0.7f;
+    cfg->fadeOutParticles = 0;
+    cfg->opacityFactor = 0.04f;
+    cfg->softParticleStepDistance = 20;
+    cfg->lightNear = 0.3f;
+    cfg->lightFar = 1000.0f;
+    cfg->lightCameraDistance = 200.0f;
+    cfg->binMode = VPE_BIN_REFERENCE;
+    cfg->marchEarlyOutTransmittance = 0.0f;
+    cfg->slabZBegin = cfg->slabZEnd = 0;
+}
+
+int vpe_create(const VpeConfig* cfg, int device, VpeContext** out) {
+    if (!cfg || !out) return VPE_E_INVALID_ARG;
+    VpeConfig c2 = *cfg;
+    normalise_slab(c2);
+    std::string why;
+    if (validate_config(c2, why)) return VPE_E_INVALID_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return VPE_E_CUDA;  // no fallback
+    if (cudaSetDevice(device) != cudaSuccess) return VPE_E_CUDA;
+    VpeContext* c = new VpeContext();
+    c->cfg = c2;
+    c->device = device;
+    memset(&c->stats, 0, sizeof(c->stats));
+    memset(&c->light, 0, sizeof(c->light));
+    c->light.rotation[3] = 1.0f;
+    c->numCells = c2.numMetavoxelsX * c2.numMetavoxelsY * c2.numMetavoxelsZ;
+    rebuild_grid_params(c);
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    c->ownStream = ok;
+    ok = ok && cudaEventCreate(&c->evFill0) == cudaSuccess && cudaEventCreate(&c->evFill1) == cudaSuccess;
+    ok = ok && cudaEventCreate(&c->evMarch0) == cudaSuccess && cudaEventCreate(&c->evMarch1) == cudaSuccess;
+    const int cells = c->numCells;
+    const size_t sheetN = (size_t)c2.numMetavoxelsX * c2.numMetavoxelsY * c2.numVoxelsInMetavoxel * c2.numVoxelsInMetavoxel;
+    ok = ok && c->dCellCount.ensure(cells) == cudaSuccess && c->dCellStart.ensure(cells + 1) == cudaSuccess;
+    ok = ok && c->dBrickOf.ensure(cells) == cudaSuccess && c->dCovered.ensure(cells) == cudaSuccess;
+    ok = ok && c->dSliceStart.ensure(c2.numMetavoxelsZ + 1) == cudaSuccess && c->dTotals.ensure(2) == cudaSuccess;
+    ok = ok && c->dBlockSums.ensure(div_up(cells, SCAN_BLOCK)) == cudaSuccess;
+    ok = ok && c->dSheet.ensure(sheetN) == cudaSuccess && c->dMvCam.ensure(cells) == cudaSuccess;
+    ok = ok && c->dRank.ensure((size_t)c2.numMetavoxelsX * c2.numMetavoxelsY) == cudaSuccess;
+    ok = ok && c->dTotalSamples.ensure(1) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->hCounts, sizeof(int) * (c2.numMetavoxelsZ + 3)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->hTotalSamples, sizeof(unsigned long long)) == cudaSuccess;
+    if (ok) {
+        ok = cudaMemset(c->dBrickOf.p, 0xff, sizeof(int) * cells) == cudaSuccess;
+        k_fill_value<<<div_up(sheetN, 256), 256>>>(c->dSheet.p, sheetN, 1.0f);
+        ok = ok && cudaDeviceSynchronize() == cudaSuccess;
+    }
+    if (!ok) {
+        cudaGetLastError();
+        vpe_destroy(c);
+        return VPE_E_CUDA;
+    }
+    *c->hTotalSamples = 0;
+    *out = c;
+    return VPE_OK;
+}
+
+int vpe_destroy(VpeContext* c) {
+    if (!c) return VPE_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->dParticles.release(); c->dPfill.release(); c->dPbin.release();
+    c->dCellCount.release(); c->dCellStart.release(); c->dBrickOf.release(); c->dCovered.release();
+    c->dSliceStart.release(); c->dPairs.release(); c->dTotals.release(); c->dBlockSums.release();
+    c->dCube.release(); c->dDepth.release(); c->dSheet.release(); c->dBricks.release(); c->dMvCam.release();
+    c->dRank.release(); c->dPixels.release(); c->dSamples.release(); c->dImage.release(); c->dImage2.release();
+    c->dTotalSamples.release(); c->dParts.release();
+    if (c->hCounts) cudaFreeHost(c->hCounts);
+    if (c->hTotalSamples) cudaFreeHost(c->hTotalSamples);
+    if (c->evFill0) cudaEventDestroy(c->evFill0);
+    if (c->evFill1) cudaEventDestroy(c->evFill1);
+    if (c->evMarch0) cudaEventDestroy(c->evMarch0);
+    if (c->evMarch1) cudaEventDestroy(c->evMarch1);
+    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return VPE_OK;
+}
+
+int vpe_set_config(VpeContext* c, const VpeConfig* cfg) {
+    if (!c || !cfg) return VPE_E_INVALID_ARG;
+    VpeConfig c2 = *cfg;
+    normalise_slab(c2);
+    std::string why;
+    if (validate_config(c2, why)) return fail(c, VPE_E_INVALID_ARG, why.c_str());
+    if (c2.numMetavoxelsX != c->cfg.numMetavoxelsX || c2.numMetavoxelsY != c->cfg.numMetavoxelsY ||
+        c2.numMetavoxelsZ != c->cfg.numMetavoxelsZ || c2.numVoxelsInMetavoxel != c->cfg.numVoxelsInMetavoxel ||
+        c2.slabZBegin != c->cfg.slabZBegin || c2.slabZEnd != c->cfg.slabZEnd)
+        return fail(c, VPE_E_INVALID_ARG, "grid dims, voxel count and slab are fixed at create");
+    c->cfg = c2;
+    rebuild_grid_params(c);  // SetGridScale re-places the metavoxels (VPR.cs:1059-1063)
+    return VPE_OK;
+}
+
+int vpe_set_light(VpeContext* c, const VpeTransform* light, const float gridCenter[3]) {
+    if (!c || !light || !gridCenter) return fail(c, VPE_E_INVALID_ARG, "null argument");
+    c->light = *light;
+    for (int i = 0; i < 3; i++) c->center[i] = gridCenter[i];
+    c->lightSet = true;
+    rebuild_grid_params(c);
+    return VPE_OK;
+}
+
+int vpe_set_displacement_cubemap(VpeContext* c, const uint8_t* r8, int edge) {
+    if (!c || !r8 || edge < 1) return fail(c, VPE_E_INVALID_ARG, "bad cubemap");
+    cudaSetDevice(c->device);
+    size_t n = (size_t)6 * edge * edge;
+    std::vector<float> f(n);
+    for (size_t i = 0; i < n; i++) f[i] = (float)r8[i] / 255.0f;  // UNORM8 -> float, as the sampler would
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->dCube.release();
+    CUDA_TRY(c, c->dCube.ensure(n));
+    CUDA_TRY(c, cudaMemcpy(c->dCube.p, f.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    c->cubeEdge = edge;
+    c->g.cubeEdge = edge;
+    c->cubeSet = true;
+    return VPE_OK;
+}
+
+int vpe_set_light_depth_map(VpeContext* c, const float* depth01) {
+    if (!c) return VPE_E_INVALID_ARG;
+    cudaSetDevice(c->device);
+    if (!depth01) { c->depthSet = false; return VPE_OK; }
+    size_t n = (size_t)c->g.NX * c->g.N * c->g.NY * c->g.N;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, c->dDepth.ensure(n));
+    CUDA_TRY(c, cudaMemcpy(c->dDepth.p, depth01, n * sizeof(float), cudaMemcpyHostToDevice));
+    c->depthSet = true;
+    return VPE_OK;
+}
+
+int vpe_set_stream(VpeContext* c, void* cudaStream) {
+    if (!c) return VPE_E_INVALID_ARG;
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->ownStream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)cudaStream;
+    c->ownStream = false;
+    return VPE_OK;
+}
+
+int vpe_fill_prepare(VpeContext* c, const VpeParticle* particles, int n, const VpeTransform* emitter, int onDevice) {
+    if (!c || (!particles && n > 0) || n < 0 || !emitter) return fail(c, VPE_E_INVALID_ARG, "bad particle input");
+    if (!c->lightSet) return fail(c, VPE_E_NOT_READY, "vpe_set_light has not been called");
+    if (!c->cubeSet) return fail(c, VPE_E_NOT_READY, "vpe_set_displacement_cubemap has not been called");
+    cudaSetDevice(c->device);
+    const float* dev = reinterpret_cast<const float*>(particles);
+    if (!onDevice) {
+        CUDA_TRY(c, c->dParticles.ensure((size_t)std::max(n, 1) * 7));
+        if (n > 0) CUDA_TRY(c, cudaMemcpyAsync(c->dParticles.p, particles, sizeof(VpeParticle) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        dev = c->dParticles.p;
+    }
+    return fill_prepare_impl(c, dev, n, emitter);
+}
+
+int vpe_fill_region(VpeContext* c, int x0, int x1, int y0, int y1) {
+    if (!c) return VPE_E_INVALID_ARG;
+    if (!c->prepared) return fail(c, VPE_E_NOT_READY, "vpe_fill_prepare has not been called");
+    if (x0 < 0 || y0 < 0 || x1 > c->g.NX || y1 > c->g.NY || x0 >= x1 || y0 >= y1) return fail(c, VPE_E_INVALID_ARG, "bad region");
+    cudaSetDevice(c->device);
+    return fill_region_impl(c, x0, x1, y0, y1);
+}
+
+int vpe_fill(VpeContext* c, const VpeParticle* particles, int n, const VpeTransform* emitter) {
+    int rc = vpe_fill_prepare(c, particles, n, emitter, 0);
+    if (rc) return rc;
+    rc = fill_region_impl(c, 0, c->g.NX, 0, c->g.NY);
+    if (rc) return rc;
+    return sync_stream(c);
+}
+
+int vpe_fill_device(VpeContext* c, const VpeParticle* particles_dev, int n, const VpeTransform* emitter) {
+    int rc = vpe_fill_prepare(c, particles_dev, n, emitter, 1);
+    if (rc) return rc;
+    return fill_region_impl(c, 0, c->g.NX, 0, c->g.NY);
+}
+
+float* vpe_light_sheet_device(VpeContext* c) { return c ? c->dSheet.p : nullptr; }
+
+int vpe_march_device(VpeContext* c, const VpeCamera* cam, float* rgba_dev, int32_t* samples_dev) {
+    if (!c || !cam || !rgba_dev) return fail(c, VPE_E_INVALID_ARG, "null argument");
+    int rc = check_ready_for_march(c);
+    if (rc) return rc;
+    cudaSetDevice(c->device);
+    return march_impl(c, cam, nullptr, 0, reinterpret_cast<float4*>(rgba_dev), nullptr, samples_dev, false);
+}
+
+int vpe_march_partial_device(VpeContext* c, const VpeCamera* cam, float* over_dev, float* under_dev, int32_t* samples_dev) {
+    if (!c || !cam || !over_dev || !under_dev) return fail(c, VPE_E_INVALID_ARG, "null argument");
+    int rc = check_ready_for_march(c);
+    if (rc) return rc;
+    cudaSetDevice(c->device);
+    return march_impl(c, cam, nullptr, 0, reinterpret_cast<float4*>(over_dev), reinterpret_cast<float4*>(under_dev), samples_dev, true);
+}
+
+int vpe_composite_device(VpeContext* c, const float* const* parts_dev, int numSlabs, int numPixels, float* rgba_dev) {
+    if (!c || !parts_dev || numSlabs < 1 || numPixels < 0 || !rgba_dev) return fail(c, VPE_E_INVALID_ARG, "bad argument");
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, c->dParts.ensure((size_t)2 * numSlabs));
+    CUDA_TRY(c, cudaMemcpyAsync(c->dParts.p, parts_dev, sizeof(float4*) * 2 * numSlabs, cudaMemcpyHostToDevice, c->stream));
+    if (numPixels > 0)
+        k_composite<<<div_up(numPixels, 256), 256, 0, c->stream>>>(c->dParts.p, numSlabs, numPixels, reinterpret_cast<float4*>(rgba_dev));
+    CUDA_TRY(c, cudaGetLastError());
+    return VPE_OK;
+}
+
+int vpe_march(VpeContext* c, const VpeCamera* cam, float* rgba, int32_t* samples) {
+    if (!c || !cam || !rgba) return fail(c, VPE_E_INVALID_ARG, "null argument");
+    int rc = check_ready_for_march(c);
+    if (rc) return rc;
+    cudaSetDevice(c->device);
+    const size_t np = (size_t)cam->width * cam->height;
+    CUDA_TRY(c, c->dImage.ensure(np));
+    if (samples) CUDA_TRY(c, c->dSamples.ensure(np));
+    rc = march_impl(c, cam, nullptr, 0, c->dImage.p, nullptr, samples ? c->dSamples.p : nullptr, false);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(rgba, c->dImage.p, np * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    if (samples) CUDA_TRY(c, cudaMemcpyAsync(samples, c->dSamples.p, np * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return sync_stream(c);
+}
+
+int vpe_march_pixels(VpeContext* c, const VpeCamera* cam, const int32_t* pixels, int n, float* rgba, int32_t* samples) {
+    if (!c || !cam || !rgba || !pixels || n < 0) return fail(c, VPE_E_INVALID_ARG, "null argument");
+    int rc = check_ready_for_march(c);
+    if (rc) return rc;
+    const int total = cam->width * cam->height;
+    for (int i = 0; i < n; i++)
+        if (pixels[i] < 0 || pixels[i] >= total) return fail(c, VPE_E_INVALID_ARG, "pixel index out of range");
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, c->dPixels.ensure(std::max(n, 1)));
+    CUDA_TRY(c, c->dImage.ensure(std::max(n, 1)));
+    CUDA_TRY(c, c->dSamples.ensure(std::max(n, 1)));
+    CUDA_TRY(c, cudaMemcpyAsync(c->dPixels.p, pixels, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    rc = march_impl(c, cam, c->dPixels.p, n, c->dImage.p, nullptr, c->dSamples.p, false);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(rgba, c->dImage.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    if (samples) CUDA_TRY(c, cudaMemcpyAsync(samples, c->dSamples.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return sync_stream(c);
+}
+
+// ---- test hooks -------------------------------------------------------------------------------
+int vpe_read_brick(VpeContext* c, int x, int y, int z, uint16_t* half4, int* covered) {
+    if (!c || !covered) return VPE_E_INVALID_ARG;
+    if (x < 0 || y < 0 || z < 0 || x >= c->g.NX || y >= c->g.NY || z >= c->g.NZ) return fail(c, VPE_E_INVALID_ARG, "metavoxel index out of range");
+    cudaSetDevice(c->device);
+    *covered = 0;
+    if (!c->filledOnce) return VPE_OK;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    int flat = (z * c->g.NY + y) * c->g.NX + x, brick = -1;
+    CUDA_TRY(c, cudaMemcpy(&brick, c->dBrickOf.p + flat, sizeof(int), cudaMemcpyDeviceToHost));
+    if (brick < 0) return VPE_OK;
+    *covered = 1;
+    size_t texels = (size_t)c->g.N * c->g.N * c->g.N;
+    if (half4) CUDA_TRY(c, cudaMemcpy(half4, c->dBricks.p + (size_t)brick * texels, texels * sizeof(uint2), cudaMemcpyDeviceToHost));
+    return VPE_OK;
+}
+
+int vpe_read_light_sheet(VpeContext* c, float* sheet) {
+    if (!c || !sheet) return VPE_E_INVALID_ARG;
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    size_t n = (size_t)c->g.NX * c->g.N * c->g.NY * c->g.N;
+    CUDA_TRY(c, cudaMemcpy(sheet, c->dSheet.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return VPE_OK;
+}
+
+int vpe_read_particle_list(VpeContext* c, int x, int y, int z, int32_t* idx, int cap, int* n) {
+    if (!c || !n) return VPE_E_INVALID_ARG;
+    if (x < 0 || y < 0 || z < 0 || x >= c->g.NX || y >= c->g.NY || z >= c->g.NZ) return fail(c, VPE_E_INVALID_ARG, "metavoxel index out of range");
+    *n = 0;
+    if (!c->prepared) return VPE_OK;
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    int flat = (z * c->g.NY + y) * c->g.NX + x, se[2];
+    CUDA_TRY(c, cudaMemcpy(se, c->dCellStart.p + flat, sizeof(int) * 2, cudaMemcpyDeviceToHost));
+    *n = se[1] - se[0];
+    int take = std::min(*n, cap);
+    if (idx && take > 0) CUDA_TRY(c, cudaMemcpy(idx, c->dPairs.p + se[0], sizeof(int) * take, cudaMemcpyDeviceToHost));
+    return VPE_OK;
+}
+
+int vpe_read_metavoxel_position(VpeContext* c, int x, int y, int z, float pos[3]) {
+    if (!c || !pos) return VPE_E_INVALID_ARG;
+    if (!c->lightSet) return fail(c, VPE_E_NOT_READY, "vpe_set_light has not been called");
+    if (x < 0 || y < 0 || z < 0 || x >= c->g.NX || y >= c->g.NY || z >= c->g.NZ) return fail(c, VPE_E_INVALID_ARG, "metavoxel index out of range");
+    F3 p = mv_center(c->g, x, y, z);  // same routine the kernels call
+    pos[0] = p.x; pos[1] = p.y; pos[2] = p.z;
+    return VPE_OK;
+}
+
+int vpe_get_stats(VpeContext* c, VpeStats* s) {
+    if (!c || !s) return VPE_E_INVALID_ARG;
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->fillTimed) cudaEventElapsedTime(&c->stats.fillMs, c->evFill0, c->evFill1);
+    if (c->marchTimed) {
+        cudaEventElapsedTime(&c->stats.marchMs, c->evMarch0, c->evMarch1);
+        c->stats.raySamples = (int64_t)*c->hTotalSamples;
+    }
+    c->stats.brickPoolBytes = (int64_t)(c->dBricks.cap * sizeof(uint2));
+    *s = c->stats;
+    return VPE_OK;
+}
+
+const char* vpe_last_error(VpeContext* c) { return c ? c->err.c_str() : "null context"; }
+int vpe_abi_version(void) { return VPE_ABI_VERSION; }
+const char* vpe_backend(void) { return "cuda"; }
+
+}  // extern "C"
