@@ -103,6 +103,8 @@ typedef struct VpeStats {
     float fillMs, marchMs;       /* device time of the last fill / march (CUDA events);
                                     wall time in the oracle                                 */
     int64_t brickPoolBytes;
+    float fillKernelMs;          /* device time of the per-slice fill kernels alone (last fill)  */
+    float marchKernelMs;         /* device time of the march kernel alone (last march)           */
 } VpeStats;
 
 typedef struct VpeContext VpeContext;
@@ -171,6 +173,12 @@ int vpe_march_partial_device(VpeContext* ctx, const VpeCamera* cam, float* over_
  * parts_dev[2*r+1] = under of slab r (device pointers, numPixels*4 floats each). */
 int vpe_composite_device(VpeContext* ctx, const float* const* parts_dev, int numSlabs,
                          int numPixels, float* rgba_dev);
+
+/* ---- measurement ----
+ * Number of distinct volume texels in the union of all samples' 8-texel trilinear footprints for
+ * this camera (the march's compulsory read set = 8 B x this + 16 B x pixels).
+ * Runs an instrumented march (never timed). */
+int vpe_march_footprint(VpeContext* ctx, const VpeCamera* cam, int64_t* uniqueTexels);
 
 /* ---- test hooks ---- */
 /* brick (x,y,z) as N*N*N half4 in [slice][row][col] order (≙ mvFillTextures[z,y,x], VPR.cs:312);

@@ -561,7 +561,13 @@ struct MarchPass {
     float W, H;
     float maxGridDim;
     int zBoundary;
-    struct Draw { int x, y, z; bool over; M4 C2M; };
+    struct Draw {
+        int x, y, z; bool over; M4 C2M;
+        // Rasteriser stand-in: bounding rectangle (in pixels) of the projected cube, dilated; the
+        // per-pixel decision is still the shader's slab test (March.shader:229). Only (pixel,
+        // metavoxel) pairs whose ray cannot hit the cube are skipped.
+        float px0, px1, py0, py1;
+    };
     std::vector<Draw> draws;  // in submission order, VPR.cs:667-711
 };
 
@@ -608,6 +614,25 @@ void build_march_pass(VpeContext* c, const VpeCamera* cam, MarchPass* mp) {
         d.x = xx; d.y = yy; d.z = zz; d.over = over;
         M4 mvToWorld = trs(c->mvPos[c->mvIndex(xx, yy, zz)], c->light.rotation, sv);  // VPR.cs:774-776
         d.C2M = mul(inverse(mvToWorld), mp->C2W);                                       // VPR.cs:778
+        // ≙ the vertex shader + rasteriser (March.shader:148-158, Cull Front): project the 8 corners
+        d.px0 = d.py0 = -1e30f; d.px1 = d.py1 = 1e30f;
+        double lo[2] = {1e30, 1e30}, hi[2] = {-1e30, -1e30};
+        bool behind = false;
+        M4 m2c = mul(mp->W2C, mvToWorld);
+        for (int k = 0; k < 8 && !behind; k++) {
+            V3 corner = v3((k & 1) ? 0.5f : -0.5f, (k & 2) ? 0.5f : -0.5f, (k & 4) ? 0.5f : -0.5f);
+            V3 cs = mul4(m2c, corner, 1.0f);
+            if (cs.z > -1e-3f * c->cfg.mvScale) { behind = true; break; }
+            double sx = (double)cs.x / -(double)cs.z / ((double)mp->tanHalfFov * (double)(mp->W / mp->H));
+            double sy = (double)cs.y / -(double)cs.z / (double)mp->tanHalfFov;
+            double fx = 0.5 * (double)mp->W * (1.0 + sx), fy = 0.5 * (double)mp->H * (1.0 + sy);
+            lo[0] = std::min(lo[0], fx); hi[0] = std::max(hi[0], fx);
+            lo[1] = std::min(lo[1], fy); hi[1] = std::max(hi[1], fy);
+        }
+        if (!behind) {
+            d.px0 = (float)(lo[0] - 1.5); d.px1 = (float)(hi[0] + 1.5);
+            d.py0 = (float)(lo[1] - 1.5); d.py1 = (float)(hi[1] + 1.5);
+        }
         mp->draws.push_back(d);
     };
     for (int zz = 0; zz <= zB; zz++)                       // VPR.cs:667-680
@@ -684,7 +709,8 @@ RaySetup ray_setup(const VpeContext* c, const MarchPass* mp, int px, int py) {
 
 // March.shader:166-302 frag for one (pixel, metavoxel); returns false when the shader returns
 // "seethrough" before the loop (no intersection).  src = (rgb, 1 - transmittance).
-bool march_frag(const VpeContext* c, const RaySetup& rs, const MarchPass::Draw& dr, float src[4], int* samples) {
+bool march_frag(const VpeContext* c, const RaySetup& rs, const MarchPass::Draw& dr, float src[4], int* samples,
+                std::vector<uint8_t>* footprint = nullptr) {
     const int N = c->N();
     V3 o = mul4(dr.C2M, rs.start, 1.0f);                     // :217
     V3 d = normalize_hlsl(mul4(dr.C2M, rs.dir, 0.0f));       // :218
@@ -712,6 +738,14 @@ bool march_frag(const VpeContext* c, const RaySetup& rs, const MarchPass::Draw& 
         sp = v3(sp.x * scale + borderVoxelOffset, sp.y * scale + borderVoxelOffset, sp.z * scale + borderVoxelOffset);  // :258
         float vc[4];
         sample_brick(brick, N, sp, vc);                              // :262
+        if (footprint) {  // measurement: mark the sample's 8-texel trilinear footprint
+            const float Nf = (float)N;
+            int ix = (int)floorf(sp.x * Nf - 0.5f), iy = (int)floorf(sp.y * Nf - 0.5f), iz = (int)floorf(sp.z * Nf - 0.5f);
+            for (int k = 0; k < 8; k++) {
+                int x = wrap(ix + (k & 1), N), y = wrap(iy + ((k >> 1) & 1), N), z = wrap(iz + (k >> 2), N);
+                (*footprint)[((size_t)z * N + y) * N + x] = 1;
+            }
+        }
         float density = vc[3];
         if (stepIndex - tCamera < c->cfg.softParticleStepDistance)   // :267
             density *= (float)(stepIndex - tCamera) * softRcp;       // :269
@@ -738,7 +772,7 @@ inline void rop_blend(float dst[4], const float src[4], bool over) {
 }
 
 int march_pixels_impl(VpeContext* c, const VpeCamera* cam, const int32_t* pixels, int n, float* rgba, int32_t* samples,
-                      float* overPart, float* underPart) {
+                      float* overPart, float* underPart, std::vector<std::vector<uint8_t>>* footprints = nullptr) {
     if (!c->lightSet) return fail(c, VPE_E_NOT_READY, "vpe_set_light has not been called");
     if (!c->prepared) return fail(c, VPE_E_NOT_READY, "vpe_fill has not been called");
     if (cam->width < 1 || cam->height < 1) return fail(c, VPE_E_INVALID_ARG, "bad image size");
@@ -749,7 +783,7 @@ int march_pixels_impl(VpeContext* c, const VpeCamera* cam, const int32_t* pixels
     const int count = pixels ? n : total;
     int64_t totalSamples = 0;
     int bad = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(+ : totalSamples)
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : totalSamples) if (!footprints)
     for (int i = 0; i < count; i++) {
         int pix = pixels ? pixels[i] : i;
         if (pix < 0 || pix >= total) { bad = 1; continue; }
@@ -758,8 +792,10 @@ int march_pixels_impl(VpeContext* c, const VpeCamera* cam, const int32_t* pixels
         float dst[4] = {0, 0, 0, 0};      // VPR.cs:171-172 clear colour
         float dOver[4] = {0, 0, 0, 0}, dUnder[4] = {0, 0, 0, 0};
         int ns = 0;
+        const float pcx = (float)px + 0.5f, pcy = (float)py + 0.5f;
         for (const MarchPass::Draw& dr : mp.draws) {
             float src[4];
+            if (pcx < dr.px0 || pcx > dr.px1 || pcy < dr.py0 || pcy > dr.py1) continue;  // not rasterised
             if (!c->filled[c->mvIndex(dr.x, dr.y, dr.z)]) {
                 // region-filled oracle (vpe_fill_region on a subset): a ray may only enter filled metavoxels
                 V3 o = mul4(dr.C2M, rs.start, 1.0f);
@@ -768,7 +804,12 @@ int march_pixels_impl(VpeContext* c, const VpeCamera* cam, const int32_t* pixels
                 if (intersect_box(o, d, &t1, &t2)) bad = 2;
                 continue;
             }
-            if (!march_frag(c, rs, dr, src, &ns)) continue;  // seethrough: blending (0,0,0,0) is the identity
+            std::vector<uint8_t>* fp = nullptr;
+            if (footprints) {
+                fp = &(*footprints)[c->mvIndex(dr.x, dr.y, dr.z)];
+                if (fp->empty()) fp->assign((size_t)c->N() * c->N() * c->N(), 0);
+            }
+            if (!march_frag(c, rs, dr, src, &ns, fp)) continue;  // seethrough: blending (0,0,0,0) is the identity
             rop_blend(dst, src, dr.over);
             if (overPart && dr.over) rop_blend(dOver, src, true);
             if (underPart && !dr.over) rop_blend(dUnder, src, false);
@@ -927,6 +968,18 @@ int vpe_march_pixels(VpeContext* c, const VpeCamera* cam, const int32_t* pixels,
     return march_pixels_impl(c, cam, pixels, n, rgba, samples, nullptr, nullptr);
 }
 
+int vpe_march_footprint(VpeContext* c, const VpeCamera* cam, int64_t* uniqueTexels) {
+    if (!c || !cam || !uniqueTexels) return fail(c, VPE_E_INVALID_ARG, "null argument");
+    std::vector<std::vector<uint8_t>> fps(c->lists.size());
+    std::vector<float> rgba((size_t)cam->width * cam->height * 4);
+    int rc = march_pixels_impl(c, cam, nullptr, 0, rgba.data(), nullptr, nullptr, nullptr, &fps);
+    int64_t n = 0;
+    for (auto& f : fps)
+        for (uint8_t b : f) n += b;
+    *uniqueTexels = n;
+    return rc;
+}
+
 // Oracle-only: slab partial images on the host (same semantics as vpe_march_partial_device).
 int vpe_ref_march_partial(VpeContext* c, const VpeCamera* cam, float* over, float* under, int32_t* samples) {
     if (!c || !cam || !over || !under) return fail(c, VPE_E_INVALID_ARG, "null argument");
@@ -1008,6 +1061,8 @@ int vpe_get_stats(VpeContext* c, VpeStats* s) {
     int64_t bytes = 0;
     for (auto& b : c->bricks) bytes += (int64_t)b.size() * 2;
     s->brickPoolBytes = bytes;
+    s->fillKernelMs = s->fillMs;
+    s->marchKernelMs = s->marchMs;
     return VPE_OK;
 }
 

@@ -58,6 +58,7 @@ class VpeStats(C.Structure):
         ("zBoundary", C.c_int32), ("fillLaunches", C.c_int32), ("marchLaunches", C.c_int32),
         ("fillMs", C.c_float), ("marchMs", C.c_float),
         ("brickPoolBytes", C.c_int64),
+        ("fillKernelMs", C.c_float), ("marchKernelMs", C.c_float),
     ]
 
 
@@ -85,6 +86,7 @@ PROTOTYPES = {
     "vpe_light_sheet_device": (_P, [_P]),
     "vpe_march_partial_device": (C.c_int, [_P, C.POINTER(VpeCamera), _P, _P, _P]),
     "vpe_composite_device": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_int, _P]),
+    "vpe_march_footprint": (C.c_int, [_P, C.POINTER(VpeCamera), C.POINTER(C.c_int64)]),
     "vpe_read_brick": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
     "vpe_read_light_sheet": (C.c_int, [_P, _P]),
     "vpe_read_particle_list": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_int)]),

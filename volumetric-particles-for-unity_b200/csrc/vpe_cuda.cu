@@ -86,6 +86,7 @@ struct VpeContext {
     int numCells = 0;
     // timing
     cudaEvent_t evFill0 = nullptr, evFill1 = nullptr, evMarch0 = nullptr, evMarch1 = nullptr;
+    cudaEvent_t evFillK0 = nullptr, evMarchK0 = nullptr, evMarchK1 = nullptr;
     bool fillTimed = false, marchTimed = false;
     VpeStats stats;
 };
@@ -245,6 +246,7 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1) {
     a.sheet = c->dSheet.p; a.bricks = c->dBricks.p;
     a.x0 = x0; a.x1 = x1; a.y0 = y0; a.y1 = y1;
     const int tiles = div_up((long long)g.N * g.N, FILL_THREADS);
+    CUDA_TRY(c, cudaEventRecord(c->evFillK0, c->stream));
     for (int zz = g.z0; zz < g.z1; zz++) {  // nearest the light first (VPR.cs:505)
         int count = c->sliceStart[zz + 1] - c->sliceStart[zz];
         if (count <= 0) continue;           // VPR.cs:511
@@ -265,7 +267,7 @@ struct SortData {  // ≙ MetavoxelSortData, VPR.cs:43-62
 };
 
 int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nPixels, float4* rgbaDev, float4* underDev,
-               int* samplesDev, bool partial) {
+               int* samplesDev, bool partial, unsigned* footprint = nullptr) {
     GridParams& g = c->g;
     const VpeConfig& k = c->cfg;
     if (cam->width < 1 || cam->height < 1) return fail(c, VPE_E_INVALID_ARG, "bad image size");
@@ -342,13 +344,17 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     MarchArgs a;
     a.mvCam = c->dMvCam.p; a.rankAsc = c->dRank.p; a.bricks = c->dBricks.p; a.pixels = pixelsDev;
     a.rgba = rgbaDev; a.under = underDev; a.samples = samplesDev; a.totalSamples = c->dTotalSamples.p;
+    a.footprint = footprint;
     dim3 grid, block(128);
     if (pixelsDev) grid = dim3(div_up(nPixels, 128));
     else grid = dim3(div_up(cam->width, 16), div_up(cam->height, 8));
+    CUDA_TRY(c, cudaEventRecord(c->evMarchK0, c->stream));
     if (m.numPixels > 0) {
-        if (partial) k_march<true><<<grid, block, 0, c->stream>>>(g, m, a);
-        else k_march<false><<<grid, block, 0, c->stream>>>(g, m, a);
+        if (footprint) k_march<false, true><<<grid, block, 0, c->stream>>>(g, m, a);
+        else if (partial) k_march<true, false><<<grid, block, 0, c->stream>>>(g, m, a);
+        else k_march<false, false><<<grid, block, 0, c->stream>>>(g, m, a);
     }
+    CUDA_TRY(c, cudaEventRecord(c->evMarchK1, c->stream));
     c->stats.marchLaunches = 2;
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaMemcpyAsync(c->hTotalSamples, c->dTotalSamples.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
@@ -410,6 +416,7 @@ int vpe_create(const VpeConfig* cfg, int device, VpeContext** out) {
     c->ownStream = ok;
     ok = ok && cudaEventCreate(&c->evFill0) == cudaSuccess && cudaEventCreate(&c->evFill1) == cudaSuccess;
     ok = ok && cudaEventCreate(&c->evMarch0) == cudaSuccess && cudaEventCreate(&c->evMarch1) == cudaSuccess;
+    ok = ok && cudaEventCreate(&c->evFillK0) == cudaSuccess && cudaEventCreate(&c->evMarchK0) == cudaSuccess && cudaEventCreate(&c->evMarchK1) == cudaSuccess;
     const int cells = c->numCells;
     const size_t sheetN = (size_t)c2.numMetavoxelsX * c2.numMetavoxelsY * c2.numVoxelsInMetavoxel * c2.numVoxelsInMetavoxel;
     ok = ok && c->dCellCount.ensure(cells) == cudaSuccess && c->dCellStart.ensure(cells + 1) == cudaSuccess;
@@ -452,6 +459,9 @@ int vpe_destroy(VpeContext* c) {
     if (c->evFill1) cudaEventDestroy(c->evFill1);
     if (c->evMarch0) cudaEventDestroy(c->evMarch0);
     if (c->evMarch1) cudaEventDestroy(c->evMarch1);
+    if (c->evFillK0) cudaEventDestroy(c->evFillK0);
+    if (c->evMarchK0) cudaEventDestroy(c->evMarchK0);
+    if (c->evMarchK1) cudaEventDestroy(c->evMarchK1);
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return VPE_OK;
@@ -618,6 +628,37 @@ int vpe_march_pixels(VpeContext* c, const VpeCamera* cam, const int32_t* pixels,
     return sync_stream(c);
 }
 
+int vpe_march_footprint(VpeContext* c, const VpeCamera* cam, int64_t* uniqueTexels) {
+    if (!c || !cam || !uniqueTexels) return fail(c, VPE_E_INVALID_ARG, "null argument");
+    int rc = check_ready_for_march(c);
+    if (rc) return rc;
+    cudaSetDevice(c->device);
+    const size_t np = (size_t)cam->width * cam->height;
+    const size_t texels = (size_t)c->nCovered * c->g.N * c->g.N * c->g.N;
+    const size_t words = texels / 32 + 1;
+    DevBuf<unsigned> bitmap;
+    DevBuf<unsigned long long> count;
+    CUDA_TRY(c, c->dImage.ensure(np));
+    CUDA_TRY(c, bitmap.ensure(words));
+    CUDA_TRY(c, count.ensure(1));
+    CUDA_TRY(c, cudaMemsetAsync(bitmap.p, 0, words * sizeof(unsigned), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(count.p, 0, sizeof(unsigned long long), c->stream));
+    rc = march_impl(c, cam, nullptr, 0, c->dImage.p, nullptr, nullptr, false, bitmap.p);
+    if (rc == VPE_OK) {
+        k_popcount<<<148 * 8, 256, 0, c->stream>>>(bitmap.p, words, count.p);
+        unsigned long long h = 0;
+        cudaError_t e = cudaMemcpyAsync(&h, count.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = VPE_E_CUDA; }
+        *uniqueTexels = (int64_t)h;
+    }
+    cudaStreamSynchronize(c->stream);
+    bitmap.release();
+    count.release();
+    c->marchTimed = false;  // an instrumented march is never reported as a timing
+    return rc;
+}
+
 // ---- test hooks -------------------------------------------------------------------------------
 int vpe_read_brick(VpeContext* c, int x, int y, int z, uint16_t* half4, int* covered) {
     if (!c || !covered) return VPE_E_INVALID_ARG;
@@ -672,9 +713,13 @@ int vpe_get_stats(VpeContext* c, VpeStats* s) {
     if (!c || !s) return VPE_E_INVALID_ARG;
     cudaSetDevice(c->device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (c->fillTimed) cudaEventElapsedTime(&c->stats.fillMs, c->evFill0, c->evFill1);
+    if (c->fillTimed) {
+        cudaEventElapsedTime(&c->stats.fillMs, c->evFill0, c->evFill1);
+        cudaEventElapsedTime(&c->stats.fillKernelMs, c->evFillK0, c->evFill1);
+    }
     if (c->marchTimed) {
         cudaEventElapsedTime(&c->stats.marchMs, c->evMarch0, c->evMarch1);
+        cudaEventElapsedTime(&c->stats.marchKernelMs, c->evMarchK0, c->evMarchK1);
         c->stats.raySamples = (int64_t)*c->hTotalSamples;
     }
     c->stats.brickPoolBytes = (int64_t)(c->dBricks.cap * sizeof(uint2));

@@ -214,6 +214,13 @@ class Engine:
         self._check(self.lib.vpe_composite_device(self._ctx, arr, len(part_ptrs) // 2, int(num_pixels),
                                                   C.c_void_p(int(rgba_ptr))))
 
+    def march_footprint(self, camera):
+        """Distinct texels touched by the march's trilinear footprints (measurement, never timed)."""
+        c = _camera(camera)
+        n = C.c_int64(0)
+        self._check(self.lib.vpe_march_footprint(self._ctx, C.byref(c), C.byref(n)))
+        return n.value
+
     # -- test hooks -----------------------------------------------------------------------
     def read_brick(self, x, y, z):
         """half4 brick as uint16 [N][N][N][4] (slice, row, col, rgba) or None when not covered."""
