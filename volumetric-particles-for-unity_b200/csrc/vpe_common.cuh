@@ -72,6 +72,7 @@ struct MarchParams {
     int numPixels;               // W*H or the length of the pixel list
     int maxSamplesPerMv;         // hang guard: (int)(sqrt(3)/stepSize) + 2
     int wrap;                    // border == 0: repeat addressing can trigger (VPR.cs:770)
+    int tileLog2W;               // warp pixel tile = 2^tileLog2W x (32 >> tileLog2W)
 };
 
 }  // namespace vpe

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -345,14 +346,39 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     a.mvCam = c->dMvCam.p; a.rankAsc = c->dRank.p; a.bricks = c->dBricks.p; a.pixels = pixelsDev;
     a.rgba = rgbaDev; a.under = underDev; a.samples = samplesDev; a.totalSamples = c->dTotalSamples.p;
     a.footprint = footprint;
+    // Warp pixel tile: follow the bricks' x axis (their 128-byte rows) on screen. Brick x in camera
+    // space is column 0 of TRS(., lightRot, s)^-1 ... = row-space of C2Mlin: d(brick x)/d(camera x,y).
+    {
+        const float ax = fabsf(m.C2Mlin[0][0]), ay = fabsf(m.C2Mlin[0][1]), az = fabsf(m.C2Mlin[0][2]);
+        int lw = 3;                                   // 8x4: no preferred direction
+        if (ax >= 2.0f * ay && ax >= az) lw = 5;      // 32x1 strips along screen x
+        else if (ay >= 2.0f * ax && ay >= az) lw = 0; // 1x32 strips along screen y
+        const char* ov = getenv("VPE_MARCH_TILE_LOG2W");
+        if (ov && ov[0] >= '0' && ov[0] <= '5' && !ov[1]) lw = ov[0] - '0';
+        m.tileLog2W = lw;
+    }
     dim3 grid, block(128);
     if (pixelsDev) grid = dim3(div_up(nPixels, 128));
-    else grid = dim3(div_up(cam->width, 16), div_up(cam->height, 8));
+    else {
+        const int lw = m.tileLog2W, tw = 1 << lw, th = 32 >> lw;
+        const int cw = lw >= 4 ? tw : (lw <= 1 ? 4 * tw : 2 * tw), ch = lw >= 4 ? 4 * th : (lw <= 1 ? th : 2 * th);
+        grid = dim3(div_up(cam->width, cw), div_up(cam->height, ch));
+    }
     CUDA_TRY(c, cudaEventRecord(c->evMarchK0, c->stream));
     if (m.numPixels > 0) {
-        if (footprint) k_march<false, true><<<grid, block, 0, c->stream>>>(g, m, a);
-        else if (partial) k_march<true, false><<<grid, block, 0, c->stream>>>(g, m, a);
-        else k_march<false, false><<<grid, block, 0, c->stream>>>(g, m, a);
+        const bool legacy = m.wrap || getenv("VPE_MARCH_LEGACY");
+#define VPE_LAUNCH_MARCH(NT)                                                                   \
+    do {                                                                                       \
+        if (partial) k_march<NT, true, false><<<grid, block, 0, c->stream>>>(g, m, a);         \
+        else k_march<NT, false, false><<<grid, block, 0, c->stream>>>(g, m, a);                \
+    } while (0)
+        if (footprint) k_march<-1, false, true><<<grid, block, 0, c->stream>>>(g, m, a);
+        else if (legacy) VPE_LAUNCH_MARCH(-1);
+        else if (g.N == 32) VPE_LAUNCH_MARCH(32);
+        else if (g.N == 64) VPE_LAUNCH_MARCH(64);
+        else if (g.N == 8) VPE_LAUNCH_MARCH(8);
+        else VPE_LAUNCH_MARCH(0);
+#undef VPE_LAUNCH_MARCH
     }
     CUDA_TRY(c, cudaEventRecord(c->evMarchK1, c->stream));
     c->stats.marchLaunches = 2;
