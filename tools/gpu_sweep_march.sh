@@ -1,19 +1,20 @@
 #!/bin/bash
-# GPU experiment: parity tests, then cfg3 bench for march variants (legacy loop, fast loop, warp tile shapes).
+# GPU experiment: parity tests, then cfg3 bench for march variants.
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/sweep_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/sweep_pytest.log
 tail -5 gpurun_out/sweep_pytest.log
-VPE_MARCH_LEGACY=1 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/sweep_legacy.json 2> gpurun_out/sweep_legacy.err
-for lw in 0 2 3 4 5; do
-  VPE_MARCH_TILE_LOG2W=$lw python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/sweep_fast_lw$lw.json 2> gpurun_out/sweep_fast_lw$lw.err
-done
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/sweep_fast_auto.json 2> gpurun_out/sweep_fast_auto.err
+rm -f gpurun_out/sweep_*.json
+run() { name=$1; shift; env "$@" python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/sweep_$name.json 2> gpurun_out/sweep_$name.err; }
+run noskip_lw3 VPE_MARCH_NO_SKIP=1 VPE_MARCH_TILE_LOG2W=3
+run skip_lw3 VPE_MARCH_TILE_LOG2W=3
+run skip_lw4 VPE_MARCH_TILE_LOG2W=4
+run skip_lw5 VPE_MARCH_TILE_LOG2W=5
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/sweep_*.json')):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
-        print(f, 'march_ms=%.3f kern=%.3f fill_ms=%.3f samples=%d frac=%.4f' % (d['march']['ms'], d['march']['kernel_ms'], d['fill']['ms'], d['march']['ray_samples'], d['roofline']['frac']))
+        print(f, 'march_ms=%.3f kern=%.3f fill_ms=%.3f fill_kern=%.3f samples=%d frac=%.4f e2e_march=%.2f e2e_fill=%.2f' % (d['march']['ms'], d['march']['kernel_ms'], d['fill']['ms'], d['fill']['kernel_ms'], d['march']['ray_samples'], d['roofline']['frac'], d['e2e']['march_ms'], d['e2e']['fill_ms']))
     except Exception as e:
         print(f, 'ERR', e)
 PY

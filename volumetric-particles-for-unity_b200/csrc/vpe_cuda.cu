@@ -72,6 +72,8 @@ struct VpeContext {
     DevBuf<int2> dBlockSums;
     DevBuf<float> dCube, dDepth, dSheet;
     DevBuf<uint2> dBricks;
+    DevBuf<unsigned> dOcc;           // occupancy cells per brick (skip empty space in the march)
+    int occCells = 0;                // 0 = occupancy off (N > 128)
     DevBuf<float4> dMvCam;
     DevBuf<int> dRank, dPixels, dSamples;
     DevBuf<float4> dImage, dImage2;
@@ -226,6 +228,11 @@ int fill_prepare_impl(VpeContext* c, const float* particlesDev, int n, const Vpe
             return fail(c, VPE_E_OUT_OF_MEMORY, "brick pool does not fit in device memory");
         }
     }
+    if (c->occCells) {
+        const size_t words = std::max<size_t>(1, (size_t)c->nCovered * c->occCells * c->occCells);
+        CUDA_TRY(c, c->dOcc.ensure(words + words / 16));
+        CUDA_TRY(c, cudaMemsetAsync(c->dOcc.p, 0, words * sizeof(unsigned), c->stream));
+    }
     // VPR.cs:498-499: clear the light propagation texture to 1
     const size_t sheetN = (size_t)g.NX * g.N * g.NY * g.N;
     k_fill_value<<<std::min(div_up(sheetN, 256), 148 * 8), 256, 0, c->stream>>>(c->dSheet.p, sheetN, 1.0f);
@@ -245,6 +252,7 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1) {
     a.covered = c->dCovered.p; a.sliceStart = c->dSliceStart.p; a.cellStart = c->dCellStart.p; a.pairs = c->dPairs.p;
     a.pfill = c->dPfill.p; a.cube = c->dCube.p; a.depth = c->depthSet ? c->dDepth.p : nullptr;
     a.sheet = c->dSheet.p; a.bricks = c->dBricks.p;
+    a.occ = c->occCells ? c->dOcc.p : nullptr; a.occCells = c->occCells;
     a.x0 = x0; a.x1 = x1; a.y0 = y0; a.y1 = y1;
     const int tiles = div_up((long long)g.N * g.N, FILL_THREADS);
     CUDA_TRY(c, cudaEventRecord(c->evFillK0, c->stream));
@@ -346,6 +354,8 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     a.mvCam = c->dMvCam.p; a.rankAsc = c->dRank.p; a.bricks = c->dBricks.p; a.pixels = pixelsDev;
     a.rgba = rgbaDev; a.under = underDev; a.samples = samplesDev; a.totalSamples = c->dTotalSamples.p;
     a.footprint = footprint;
+    const bool skip = c->occCells > 0 && !getenv("VPE_MARCH_NO_SKIP");
+    a.occ = skip ? c->dOcc.p : nullptr; a.occCells = c->occCells;
     // Warp pixel tile: follow the bricks' x axis (their 128-byte rows) on screen. Brick x in camera
     // space is column 0 of TRS(., lightRot, s)^-1 ... = row-space of C2Mlin: d(brick x)/d(camera x,y).
     {
@@ -367,10 +377,12 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     CUDA_TRY(c, cudaEventRecord(c->evMarchK0, c->stream));
     if (m.numPixels > 0) {
         const bool legacy = m.wrap || getenv("VPE_MARCH_LEGACY");
-#define VPE_LAUNCH_MARCH(NT)                                                                   \
-    do {                                                                                       \
-        if (partial) k_march<NT, true, false><<<grid, block, 0, c->stream>>>(g, m, a);         \
-        else k_march<NT, false, false><<<grid, block, 0, c->stream>>>(g, m, a);                \
+#define VPE_LAUNCH_MARCH(NT)                                                                          \
+    do {                                                                                              \
+        if (partial && skip) k_march<NT, true, false, true><<<grid, block, 0, c->stream>>>(g, m, a);  \
+        else if (partial) k_march<NT, true, false, false><<<grid, block, 0, c->stream>>>(g, m, a);    \
+        else if (skip) k_march<NT, false, false, true><<<grid, block, 0, c->stream>>>(g, m, a);       \
+        else k_march<NT, false, false, false><<<grid, block, 0, c->stream>>>(g, m, a);                \
     } while (0)
         if (footprint) k_march<-1, false, true><<<grid, block, 0, c->stream>>>(g, m, a);
         else if (legacy) VPE_LAUNCH_MARCH(-1);
@@ -437,6 +449,7 @@ int vpe_create(const VpeConfig* cfg, int device, VpeContext** out) {
     memset(&c->light, 0, sizeof(c->light));
     c->light.rotation[3] = 1.0f;
     c->numCells = c2.numMetavoxelsX * c2.numMetavoxelsY * c2.numMetavoxelsZ;
+    c->occCells = c2.numVoxelsInMetavoxel <= 128 ? ((c2.numVoxelsInMetavoxel - 1) >> 2) + 1 : 0;
     rebuild_grid_params(c);
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     c->ownStream = ok;
@@ -476,7 +489,7 @@ int vpe_destroy(VpeContext* c) {
     c->dParticles.release(); c->dPfill.release(); c->dPbin.release();
     c->dCellCount.release(); c->dCellStart.release(); c->dBrickOf.release(); c->dCovered.release();
     c->dSliceStart.release(); c->dPairs.release(); c->dTotals.release(); c->dBlockSums.release();
-    c->dCube.release(); c->dDepth.release(); c->dSheet.release(); c->dBricks.release(); c->dMvCam.release();
+    c->dCube.release(); c->dDepth.release(); c->dSheet.release(); c->dBricks.release(); c->dOcc.release(); c->dMvCam.release();
     c->dRank.release(); c->dPixels.release(); c->dSamples.release(); c->dImage.release(); c->dImage2.release();
     c->dTotalSamples.release(); c->dParts.release();
     if (c->hCounts) cudaFreeHost(c->hCounts);
