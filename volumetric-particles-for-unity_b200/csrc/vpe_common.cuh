@@ -28,6 +28,7 @@ struct GridParams {
     int fade;                   // _FadeOutParticles
     float depthB, depthRcpA;    // Fill.shader:217-218: b, rcp(a)
     int cubeEdge;
+    float worldReach;           // bound on |coordinate| of any voxel centre of the grid (pre-test error band)
 };
 
 // world-space centre of metavoxel (x,y,z), VPR.cs:388-390
@@ -41,7 +42,8 @@ VPE_HD F3 mv_center(const GridParams& g, int x, int y, int z) {
 struct __align__(16) ParticleFill {
     float m[3][4];
     float opacity;
-    float pad[3];
+    float rejectAbove;  // 0.25 + error band of the fused pre-test (k_particle_setup); see k_fill_columns
+    float pad[2];
 };
 
 // per-particle binning record

@@ -71,6 +71,7 @@ struct VpeContext {
     DevBuf<int> dCellCount, dCellStart, dBrickOf, dCovered, dSliceStart, dPairs, dTotals;
     DevBuf<int2> dBlockSums;
     DevBuf<float> dCube, dDepth, dSheet;
+    DevBuf<float4> dCubeFp;          // bilinear footprints of the cubemap, [6][E+1][E+1]
     DevBuf<uint2> dBricks;
     DevBuf<unsigned> dOcc;           // occupancy cells per brick (skip empty space in the march)
     int occCells = 0;                // 0 = occupancy off (N > 128)
@@ -166,6 +167,11 @@ void rebuild_grid_params(VpeContext* c) {
         g.depthRcpA = 1.0f / a;
     }
     g.cubeEdge = c->cubeEdge;
+    {
+        const float maxG = (float)std::max(g.NX, std::max(g.NY, g.NZ));
+        const float cmax = std::max(fabsf(g.center.x), std::max(fabsf(g.center.y), fabsf(g.center.z)));
+        g.worldReach = cmax + 0.5f * 1.7320508f * (maxG + 2.0f) * g.sb * 1.01f;
+    }
 }
 
 int sync_stream(VpeContext* c) {
@@ -254,12 +260,20 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1) {
     a.sheet = c->dSheet.p; a.bricks = c->dBricks.p;
     a.occ = c->occCells ? c->dOcc.p : nullptr; a.occCells = c->occCells;
     a.x0 = x0; a.x1 = x1; a.y0 = y0; a.y1 = y1;
-    const int tiles = div_up((long long)g.N * g.N, FILL_THREADS);
     CUDA_TRY(c, cudaEventRecord(c->evFillK0, c->stream));
-    for (int zz = g.z0; zz < g.z1; zz++) {  // nearest the light first (VPR.cs:505)
-        int count = c->sliceStart[zz + 1] - c->sliceStart[zz];
-        if (count <= 0) continue;           // VPR.cs:511
-        k_fill_slice<<<dim3(count, tiles), FILL_THREADS, 0, c->stream>>>(g, a, zz);
+    if (getenv("VPE_FILL_LEGACY")) {
+        const int tiles = div_up((long long)g.N * g.N, FILL_THREADS);
+        for (int zz = g.z0; zz < g.z1; zz++) {  // nearest the light first (VPR.cs:505)
+            int count = c->sliceStart[zz + 1] - c->sliceStart[zz];
+            if (count <= 0) continue;           // VPR.cs:511
+            k_fill_slice<<<dim3(count, tiles), FILL_THREADS, 0, c->stream>>>(g, a, zz);
+            c->stats.fillLaunches++;
+        }
+    } else if (c->nCovered > 0) {
+        // one launch: every voxel column of the region walks all slices of the slab
+        const int warpTiles = ((g.N + 7) / 8) * ((g.N + 3) / 4);
+        k_fill_columns<<<dim3((x1 - x0) * (y1 - y0), div_up(warpTiles, FILLC_THREADS / 32)), FILLC_THREADS, 0, c->stream>>>(
+            g, a, c->dBrickOf.p, c->dCubeFp.p);
         c->stats.fillLaunches++;
     }
     CUDA_TRY(c, cudaGetLastError());
@@ -356,13 +370,10 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     a.footprint = footprint;
     const bool skip = c->occCells > 0 && !getenv("VPE_MARCH_NO_SKIP");
     a.occ = skip ? c->dOcc.p : nullptr; a.occCells = c->occCells;
-    // Warp pixel tile: follow the bricks' x axis (their 128-byte rows) on screen. Brick x in camera
-    // space is column 0 of TRS(., lightRot, s)^-1 ... = row-space of C2Mlin: d(brick x)/d(camera x,y).
+    // Warp pixel tile. Measured on cfg3 (profiles/): the compact 8x4 tile wins over strips that follow
+    // the bricks' 128-byte rows, because lanes of a strip sit in different bricks and diverge.
     {
-        const float ax = fabsf(m.C2Mlin[0][0]), ay = fabsf(m.C2Mlin[0][1]), az = fabsf(m.C2Mlin[0][2]);
-        int lw = 3;                                   // 8x4: no preferred direction
-        if (ax >= 2.0f * ay && ax >= az) lw = 5;      // 32x1 strips along screen x
-        else if (ay >= 2.0f * ax && ay >= az) lw = 0; // 1x32 strips along screen y
+        int lw = 3;
         const char* ov = getenv("VPE_MARCH_TILE_LOG2W");
         if (ov && ov[0] >= '0' && ov[0] <= '5' && !ov[1]) lw = ov[0] - '0';
         m.tileLog2W = lw;
@@ -489,7 +500,7 @@ int vpe_destroy(VpeContext* c) {
     c->dParticles.release(); c->dPfill.release(); c->dPbin.release();
     c->dCellCount.release(); c->dCellStart.release(); c->dBrickOf.release(); c->dCovered.release();
     c->dSliceStart.release(); c->dPairs.release(); c->dTotals.release(); c->dBlockSums.release();
-    c->dCube.release(); c->dDepth.release(); c->dSheet.release(); c->dBricks.release(); c->dOcc.release(); c->dMvCam.release();
+    c->dCube.release(); c->dCubeFp.release(); c->dDepth.release(); c->dSheet.release(); c->dBricks.release(); c->dOcc.release(); c->dMvCam.release();
     c->dRank.release(); c->dPixels.release(); c->dSamples.release(); c->dImage.release(); c->dImage2.release();
     c->dTotalSamples.release(); c->dParts.release();
     if (c->hCounts) cudaFreeHost(c->hCounts);
@@ -540,6 +551,22 @@ int vpe_set_displacement_cubemap(VpeContext* c, const uint8_t* r8, int edge) {
     c->dCube.release();
     CUDA_TRY(c, c->dCube.ensure(n));
     CUDA_TRY(c, cudaMemcpy(c->dCube.p, f.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    {
+        // bilinear footprints with clamp addressing baked in: entry (i,j) = texels (i-1..i, j-1..j)
+        const int E1 = edge + 1;
+        std::vector<float4> fp((size_t)6 * E1 * E1);
+        auto cl = [&](int v) { return std::min(std::max(v, 0), edge - 1); };
+        for (int face = 0; face < 6; face++)
+            for (int j = 0; j < E1; j++)
+                for (int i = 0; i < E1; i++) {
+                    const float* t = f.data() + (size_t)face * edge * edge;
+                    const int x0 = cl(i - 1), x1 = cl(i), y0 = cl(j - 1), y1 = cl(j);
+                    fp[((size_t)face * E1 + j) * E1 + i] = make_float4(t[y0 * edge + x0], t[y0 * edge + x1], t[y1 * edge + x0], t[y1 * edge + x1]);
+                }
+        c->dCubeFp.release();
+        CUDA_TRY(c, c->dCubeFp.ensure(fp.size()));
+        CUDA_TRY(c, cudaMemcpy(c->dCubeFp.p, fp.data(), fp.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
     c->cubeEdge = edge;
     c->g.cubeEdge = edge;
     c->cubeSet = true;
