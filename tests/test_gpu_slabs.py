@@ -1,0 +1,119 @@
+"""GPU: the light-axis slab entry points of the C-ABI (vpe_fill_prepare / vpe_fill_region /
+vpe_march_partial_device / vpe_composite_device) against the single-context result.
+
+test_two_slab_contexts_on_one_gpu needs one GPU (two contexts share it, the sheet rows are copied
+device to device exactly as NCCL would move them); test_nccl_two_ranks needs two."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import vpe_b200
+from vpe_b200 import scenes, slabs
+from oracle_lib import oracle_engine
+from parity import RTOL, max_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene():
+    sc = scenes.make_scene("cfg1", image=(96, 80))
+    sc["camera"]["position"] = (0.3, 0.2, 0.1)
+    sc["camera"]["rotation"] = (0.0, 0.6427876, 0.0, 0.7660444)
+    return sc
+
+
+def test_two_slab_contexts_on_one_gpu():
+    import torch
+    sc = _scene()
+    cam = sc["camera"]
+    h, w = cam["height"], cam["width"]
+    one = vpe_b200.engine_for_scene(None, sc)
+    scenes.apply_scene(one, sc)
+    one.fill(sc["particles"], sc["emitter"])
+    img_one, smp_one = one.march(cam)
+
+    ranks = [slabs.CudaSlabEngine(sc, r, 2, 0) for r in range(2)]
+    bands = slabs.row_bands(ranks[0].grid[1], 4)
+    n = ranks[0].N
+    gx = ranks[0].grid[0]
+    for e in ranks:
+        e.fill_prepare(sc["particles"], sc["emitter"])
+    for (y0, y1) in bands:  # the pipeline of SlabRenderer.fill, with a device copy in place of NCCL
+        ranks[0].fill_region(0, gx, y0, y1)
+        ranks[1].sheet_tensor()[y0 * n:y1 * n].copy_(ranks[0].sheet_tensor()[y0 * n:y1 * n])
+        ranks[1].fill_region(0, gx, y0, y1)
+    torch.cuda.synchronize()
+    # volume: bit-exact with the single context, each brick on its owner
+    cov = 0
+    for z in range(ranks[0].grid[2]):
+        owner = ranks[0] if z < ranks[0].slab[1] else ranks[1]
+        for y in range(ranks[0].grid[1]):
+            for x in range(gx):
+                a, b = one.read_brick(x, y, z), owner.eng.read_brick(x, y, z)
+                assert (a is None) == (b is None)
+                if a is not None:
+                    cov += 1
+                    assert np.array_equal(a, b)
+    assert cov == one.stats()["numMetavoxelsCovered"]
+    assert np.array_equal(ranks[1].eng.read_light_sheet(), one.read_light_sheet())
+    # march: slab partials composited in slab order == single-context image (to rounding)
+    parts, total = [], 0
+    for e in ranks:
+        over, under = e.march_partial(cam)
+        parts += [over, under]
+        total += e.last_ray_samples()
+    out = ranks[0].composite([p.clone() for p in parts], h * w).reshape(h, w, 4).cpu().numpy()
+    assert total == int(smp_one.sum())
+    assert max_rel_err(out, img_one) <= 1e-5
+    ref = oracle_engine(sc)
+    scenes.apply_scene(ref, sc)
+    ref.fill(sc["particles"], sc["emitter"])
+    img_ref, _ = ref.march(cam)
+    assert max_rel_err(out, img_ref) <= RTOL
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), here):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        sc = _scene()
+        eng = slabs.CudaSlabEngine(sc, rank, world, rank)
+        r = slabs.SlabRenderer(eng, dist, fill_bands=4)
+        r.fill(sc["particles"], sc["emitter"])
+        img, total = r.march(sc["camera"])
+        torch.cuda.synchronize()
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "nccl.npz"), img=img.cpu().numpy(), total=np.int64(total))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_two_ranks(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    out = np.load(os.path.join(str(tmp_path), "nccl.npz"))
+    sc = _scene()
+    ref = oracle_engine(sc)
+    scenes.apply_scene(ref, sc)
+    ref.fill(sc["particles"], sc["emitter"])
+    img_ref, smp_ref = ref.march(sc["camera"])
+    assert int(out["total"]) == int(smp_ref.sum())
+    assert max_rel_err(out["img"], img_ref) <= RTOL

@@ -1,0 +1,334 @@
+"""Multi-GPU host logic: light-axis slabs for the fill, slab-local march + ordered compositing.
+
+One process per GPU (torch.distributed; NCCL over NVLink on the GPU box, gloo in the CPU tests).
+Rank r owns the metavoxel slices z in [r*NZ/R, (r+1)*NZ/R) — slice 0 is nearest the light
+(VPR.cs:388-390, 505) — and keeps their bricks in its own HBM; bricks never cross the link.
+
+Fill (≙ FillMetavoxels, VPR.cs:495-520).  The only dependency between slabs is the light sheet
+(lightPropogationUAV, VPR.cs:266; Fill.shader:224,250): slab r+1 needs the sheet as slab r left it.
+The metavoxel columns are cut into `tiles` bands of rows; for every band, in order, a rank receives
+the band's sheet rows from rank r-1, fills the band through its own slices (vpe_fill_region) and
+sends the rows on to rank r+1.  Bands pipeline through the ranks: after R-1 bands every GPU is busy.
+Per band the message is (rows*N) x (NX*N) fp32 — the exit-plane light sheet of north_star.
+
+March (≙ RenderMetavoxels, VPR.cs:637-713).  The reference composites metavoxels slice-major:
+slices 0..zB far-to-near with OVER, then zB+1..NZ-1 near-to-far with UNDER (VPR.cs:652-711).  A
+slab's slices are therefore one contiguous run of each phase, and because both blend equations are
+associative, a rank can march its own bricks into two premultiplied partial images (OVER part,
+UNDER part; vpe_march_partial_device) and the partials can be composited afterwards in slab order
+(vpe_composite_device).  The image is cut into R bands of rows; one all-to-all moves every rank's
+partial rows to the band's owner, which composites them; rank 0 gathers the bands.
+
+The engine adapter is what touches memory: `CudaSlabEngine` (below) wraps the CUDA library and
+device tensors; the CPU tests drive the very same `SlabRenderer` with an adapter over the oracle.
+"""
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------------------
+# pure partitioning helpers (unit-tested on CPU)
+# ------------------------------------------------------------------------------------------------
+def slab_range(num_slices, world, rank):
+    """Slices [z0, z1) owned by `rank`: contiguous, ascending with rank, sizes differ by at most 1."""
+    if not (0 <= rank < world) or world > num_slices:
+        raise ValueError("need 0 <= rank < world <= numMetavoxelsZ (got rank %d, world %d, NZ %d)" % (rank, world, num_slices))
+    return rank * num_slices // world, (rank + 1) * num_slices // world
+
+
+def row_bands(num_rows, bands):
+    """Cut [0, num_rows) into at most `bands` contiguous non-empty bands."""
+    bands = max(1, min(int(bands), num_rows))
+    return [(b * num_rows // bands, (b + 1) * num_rows // bands) for b in range(bands)]
+
+
+def image_band(height, world, rank):
+    """Image rows [r0, r1) composited by `rank`; every rank gets ceil(H/R) rows, the last may be short."""
+    per = -(-height // world)
+    return min(rank * per, height), min((rank + 1) * per, height)
+
+
+def default_fill_bands(grid, n_voxels, world, min_ctas_per_launch=512):
+    """Bands of metavoxel rows for the fill pipeline: as many as possible (the pipeline bubble is
+    (R-1)/(T+R-1)) while one band's launch still has >= min_ctas_per_launch CTAs (k_fill_columns uses
+    one CTA per 8 warp tiles of 8x4 voxel columns per metavoxel column)."""
+    if world <= 1:
+        return 1
+    gx, gy, _ = grid
+    ctas_per_row = gx * -(-(-(-n_voxels // 8) * -(-n_voxels // 4)) // 8)
+    rows_per_band = max(1, -(-min_ctas_per_launch // ctas_per_row))
+    return max(1, gy // rows_per_band)
+
+
+class SlabRenderer:
+    """fill() + march() of one rank.  `engine` is a slab engine adapter, `dist` is torch.distributed
+    (already initialised) or None for a single process."""
+
+    def __init__(self, engine, dist=None, fill_bands=None):
+        self.e = engine
+        self.dist = dist
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+        gx, gy, gz = engine.grid
+        self.z0, self.z1 = slab_range(gz, self.world, self.rank)
+        if (self.z0, self.z1) != tuple(engine.slab):
+            raise ValueError("engine owns slab %s, rank %d of %d must own %s" % (engine.slab, self.rank, self.world, (self.z0, self.z1)))
+        self.bands = row_bands(gy, fill_bands if fill_bands is not None else default_fill_bands(engine.grid, engine.N, self.world))
+
+    # -- fill -------------------------------------------------------------------------------------
+    def fill(self, particles, emitter):
+        e, d = self.e, self.dist
+        gx, gy, gz = e.grid
+        n = e.N
+        e.fill_prepare(particles, emitter)          # bins into this slab only, clears the sheet to 1
+        sheet = e.sheet_tensor()                    # (NY*N, NX*N) fp32 view of the context's sheet
+        for (y0, y1) in self.bands:
+            rows = sheet[y0 * n:y1 * n]
+            if self.rank > 0:
+                d.recv(rows, src=self.rank - 1)     # the sheet as the previous slab left it
+                e.sheet_written(y0, y1)
+            e.fill_region(0, gx, y0, y1)
+            if self.rank < self.world - 1:
+                e.sheet_read(y0, y1)
+                d.send(rows, dst=self.rank + 1)
+
+    # -- march ------------------------------------------------------------------------------------
+    def march(self, camera, gather=True):
+        """Returns (rgba, total_ray_samples): rgba is the full H x W x 4 image on rank 0 when
+        `gather` (None elsewhere), else this rank's band."""
+        e, d = self.e, self.dist
+        h, w = int(camera["height"]), int(camera["width"])
+        per = -(-h // self.world)                    # image rows per owner; the image is padded to R * per rows
+        over, under = e.march_partial(camera, per * self.world)   # 2 x (R*per, W, 4), premultiplied; rows >= H stay 0
+        samples = e.last_ray_samples()
+        if self.world == 1:
+            out = e.composite([over, under], h * w).reshape(h, w, 4)
+            return out, samples
+        # rows [q*per, (q+1)*per) of both partials go to rank q: the buffers are already laid out by owner
+        recv_over = e.buffer("recv_over", (self.world, per, w, 4))    # [slab][row][col][rgba]
+        recv_under = e.buffer("recv_under", (self.world, per, w, 4))
+        d.all_to_all_single(recv_over.view(-1), over.view(-1))
+        d.all_to_all_single(recv_under.view(-1), under.view(-1))
+        parts = []
+        for s in range(self.world):                  # ascending slab order = ascending z
+            parts += [recv_over[s], recv_under[s]]
+        band = e.composite(parts, per * w).reshape(per, w, 4)
+        total = e.all_reduce_sum(d, samples)
+        if not gather:
+            r0, r1 = image_band(h, self.world, self.rank)
+            return band[:r1 - r0], total
+        full = e.buffer("full", (self.world, per, w, 4)) if self.rank == 0 else None
+        d.gather(band, gather_list=list(full.unbind(0)) if self.rank == 0 else None, dst=0)
+        if self.rank != 0:
+            return None, total
+        return full.reshape(self.world * per, w, 4)[:h], total
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA adapter (the product path)
+# ------------------------------------------------------------------------------------------------
+class _DevPtr:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class CudaSlabEngine:
+    """Slab engine over libvpe_cuda.so with torch CUDA tensors as buffers (torch is plumbing only:
+    device memory, the current stream, and NCCL through torch.distributed)."""
+
+    def __init__(self, scene, rank, world, device):
+        import torch
+        from . import engine as _engine
+        from . import scenes
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        gz = scene["grid"][2]
+        self.slab = slab_range(gz, world, rank)
+        self.eng = _engine.engine_for_scene(None, scene, device=device, slab=self.slab)
+        self.eng.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        scenes.apply_scene(self.eng, scene)
+        self.grid, self.N = self.eng.grid, self.eng.N
+        self._sheet = None
+        self._particles = None
+        self._buffers = {}
+
+    def new_tensor(self, shape):
+        return self.torch.empty(tuple(shape), dtype=self.torch.float32, device=self.device)
+
+    def fill_prepare(self, particles, emitter):
+        t = self.torch
+        if not isinstance(particles, t.Tensor):
+            particles = t.from_numpy(np.ascontiguousarray(particles, dtype=np.float32))
+        self._particles = particles.to(self.device, non_blocking=True).contiguous()
+        self.eng.fill_prepare_device(self._particles.data_ptr(), self._particles.shape[0], emitter)
+
+    def fill_region(self, x0, x1, y0, y1):
+        self.eng.fill_region(x0, x1, y0, y1)
+
+    def sheet_tensor(self):
+        if self._sheet is None:
+            gx, gy, _ = self.grid
+            ptr = self.eng.light_sheet_device_ptr()
+            self._sheet = self.torch.as_tensor(_DevPtr(ptr, (gy * self.N, gx * self.N)), device=self.device)
+        return self._sheet
+
+    def sheet_written(self, y0, y1):  # device memory is shared with the context: nothing to copy
+        pass
+
+    def sheet_read(self, y0, y1):
+        pass
+
+    def buffer(self, name, shape):
+        """A cached, zero-initialised device tensor (reused across frames)."""
+        key = (name, tuple(shape))
+        if key not in self._buffers:
+            self._buffers[key] = self.torch.zeros(tuple(shape), dtype=self.torch.float32, device=self.device)
+        return self._buffers[key]
+
+    def march_partial(self, camera, padded_rows=None):
+        h, w = int(camera["height"]), int(camera["width"])
+        rows = max(h, padded_rows or h)
+        over, under = self.buffer("over", (rows, w, 4)), self.buffer("under", (rows, w, 4))
+        self.eng.march_partial_device(camera, over.data_ptr(), under.data_ptr())
+        return over, under
+
+    def last_ray_samples(self):
+        return int(self.eng.stats()["raySamples"])
+
+    def composite(self, parts, num_pixels):
+        out = self.buffer("composite", (num_pixels, 4))
+        self._keep = [p.contiguous() for p in parts]
+        self.eng.composite_device([p.data_ptr() for p in self._keep], num_pixels, out.data_ptr())
+        return out
+
+    def all_reduce_sum(self, dist, value):
+        t = self.torch.tensor([value], dtype=self.torch.int64, device=self.device)
+        dist.all_reduce(t)
+        return int(t.item())
+
+    def stats(self):
+        return self.eng.stats()
+
+
+# ------------------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1): strong scaling of BASELINE.json's workload over light-axis slabs
+# ------------------------------------------------------------------------------------------------
+def bench_multi_gpu(args, metric, measured_peak_hbm, ClockSampler):
+    import json
+    import os
+    import time
+
+    import torch
+    import torch.distributed as dist
+    from . import scenes
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
+    cfg_name = args.config or "cfg3"
+    sc = scenes.make_scene(cfg_name)
+    eng = CudaSlabEngine(sc, rank, world, local_rank)
+    r = SlabRenderer(eng, dist, fill_bands=args.fill_bands if getattr(args, "fill_bands", 0) else None)
+    cam = sc["camera"]
+    W, H = cam["width"], cam["height"]
+    n = sc["particles"].shape[0]
+    parts_host = torch.from_numpy(sc["particles"]).pin_memory()
+    parts_dev = parts_host.to(dev)
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    warm = max(3, args.warmup)
+    for _ in range(warm):
+        r.fill(parts_dev, sc["emitter"])
+        r.march(cam, gather=False)
+    K = max(1, args.steps)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    sync()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    total_samples = 0
+    kern_march, kern_fill = [], []
+    for i in range(K):
+        ev[i][0].record()
+        r.fill(parts_dev, sc["emitter"])
+        ev[i][1].record()
+        _, total_samples = r.march(cam, gather=False)   # (the sample-count all-reduce reads back: a sync per step)
+        ev[i][2].record()
+        st = eng.stats()
+        kern_march.append(st["marchKernelMs"])
+        kern_fill.append(st["fillKernelMs"])
+    t1.record()
+    sync()
+    clk = clocks.stop()
+    total_ms = max_over_ranks(t0.elapsed_time(t1))
+    fill_ms = max_over_ranks(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    march_ms = max_over_ranks(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    st = eng.stats()
+    voxels = sum_over_ranks(st["voxelsFilled"])
+    covered = sum_over_ranks(st["numMetavoxelsCovered"])
+    pairs = sum_over_ranks(st["numParticlePairs"])
+    pool = sum_over_ranks(st["brickPoolBytes"])
+    launches = sum_over_ranks((st["fillLaunches"] + st["marchLaunches"] + 1) * K)
+
+    # end to end with HOST buffers: pinned particles in, gathered image out on rank 0
+    rgba_host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+    e2e = []
+    for i in range(2 + K):
+        sync()
+        a = time.perf_counter()
+        r.fill(parts_host, sc["emitter"])
+        img, _ = r.march(cam, gather=True)
+        if rank == 0:
+            rgba_host.copy_(img, non_blocking=False)
+        sync()
+        if i >= 2:
+            e2e.append(time.perf_counter() - a)
+    e2e_s = max_over_ranks(float(np.mean(e2e)))
+
+    # roofline of the dominant kernel (march): this rank's compulsory read set / its kernel time
+    peak, peak_src = measured_peak_hbm()
+    uniq = sum_over_ranks(eng.eng.march_footprint(cam))
+    mk = max_over_ranks(float(np.mean(kern_march)))
+    march_bytes = 8.0 * uniq + 2 * 16.0 * W * H * world
+    ach = march_bytes / (mk * 1e-3) / 1e9
+    if rank != 0:
+        return
+    N = eng.N
+    line = {
+        "metric": metric, "value": total_samples / (march_ms * 1e-3), "unit": "ray-samples/s", "n_gpus": world, "steps": K,
+        "warmup": warm, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: %d^3 grid x %d^3 voxels, %d particles, %dx%d, %d steps/metavoxel" % (
+            cfg_name, eng.grid[0], N, n, W, H, sc["rayMarchSteps"]),
+            "parallelism": "light-axis slabs x%d (fill: sheet rows over NCCL send/recv in %d bands; march: slab-local + "
+                           "all-to-all ordered compositing)" % (world, len(r.bands)),
+            "cache": "inputs larger than L2 (brick pools %.2f GB in total); no flush between iterations" % (pool / 1e9),
+            "covered_metavoxels": int(covered), "particle_metavoxel_pairs": int(pairs)},
+        "fill": {"value": voxels / (fill_ms * 1e-3), "unit": "voxels/s", "ms": fill_ms, "voxels": int(voxels)},
+        "march": {"value": total_samples / (march_ms * 1e-3), "unit": "ray-samples/s", "ms": march_ms, "kernel_ms": mk,
+                  "ray_samples": int(total_samples)},
+        "e2e": {"value": total_samples / e2e_s, "unit": "ray-samples/s", "h2d_bytes_per_step": int(n * 28) * world,
+                "d2h_bytes_per_step": int(W * H * 16), "frame_ms": e2e_s * 1e3,
+                "note": "one fill + one march per step through SlabRenderer with pinned host particles in and the gathered "
+                        "image copied to host on rank 0; value = ray-samples / whole-frame time"},
+        "gpu_launches": int(launches), "clocks": clk,
+        "roofline": {"kernel": "k_march", "bound": "hbm", "achieved": ach, "peak": peak * world, "unit": "GB/s",
+                     "frac": ach / (peak * world), "traffic": None, "peak_source": peak_src + " x n_gpus",
+                     "algorithmic_bytes": march_bytes, "kernel_ms": mk, "distinct_texels": int(uniq)},
+        "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
