@@ -1,0 +1,104 @@
+"""The host-side mirrors of the reference's VolumetricParticleRenderer (Python: vpe_b200.renderer,
+C++: host/cpp) — frame structure (fill every updateInterval frames, march every frame), setters,
+and that both drive the C-ABI to the same image.  CPU: the host logic runs over the oracle library
+(the checker); GPU (-m gpu): the same over libvpe_cuda.so against the golden fixture."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import vpe_b200
+from vpe_b200 import scenes
+from vpe_b200.renderer import VolumetricParticleRenderer
+from parity import RTOL, max_rel_err
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def make_renderer(lib, sc):
+    r = VolumetricParticleRenderer(lib)
+    r.numMetavoxelsX, r.numMetavoxelsY, r.numMetavoxelsZ = sc["grid"]
+    r.mvScale = (sc["mvScale"],) * 3
+    r.numVoxelsInMetavoxel = sc["numVoxels"]
+    r.dirLight, r.particleSys, r.gridCenter = sc["light"], sc["emitter"], sc["gridCenter"]
+    r.Start()
+    return r
+
+
+def check_frame_structure(lib):
+    sc = scenes.make_scene("cfg1", image=(48, 48))
+    r = make_renderer(lib, sc)
+    assert r.updateInterval == 2 and not r.fadeOutParticles
+    moved = sc["particles"].copy()
+    moved[:, 0] += 0.25
+    f0 = r.OnPostRender(sc["particles"], sc["camera"])       # frame 0: fill + march
+    covered0 = r.numMetavoxelsCovered
+    f1 = r.OnPostRender(moved, sc["camera"])                 # frame 1: march only (VPR.cs:186) -> same volume
+    assert np.array_equal(f0, f1) and r.numMetavoxelsCovered == covered0
+    f2 = r.OnPostRender(moved, sc["camera"])                 # frame 2: refilled with the moved particles
+    assert not np.array_equal(f0, f2)
+    r.SetUpdateInterval(1)
+    r.SetParticleOpacityFactor(0.08)
+    f3 = r.OnPostRender(moved, sc["camera"])
+    assert f3[..., 3].sum() > f2[..., 3].sum()               # denser particles cover more
+    r.SetRayMarchSteps(16)
+    _, samples16 = r.RenderMetavoxels(sc["camera"], show_samples=True)
+    r.SetRayMarchSteps(64)
+    _, samples64 = r.RenderMetavoxels(sc["camera"], show_samples=True)
+    assert 3.5 < samples64.sum() / samples16.sum() < 4.5
+    r.SetGridScale(1.5)                                      # re-places the metavoxels (VPR.cs:1059-1063)
+    assert np.allclose(r.engine.read_metavoxel_position(5, 4, 4) - r.engine.read_metavoxel_position(4, 4, 4), [1.5, 0, 0], atol=1e-5)
+    return f0
+
+
+def build_cli(tmp_path):
+    exe = str(tmp_path / "vpe_cli")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "host", "cpp", "vpe_cli.cpp"), "-ldl"], check=True)
+    return exe
+
+
+def run_cli(exe, lib_path, tmp_path, frames):
+    sc = scenes.make_scene("cfg1", image=(48, 48))
+    pfile, out = str(tmp_path / "particles.f32"), str(tmp_path / "out.rgba")
+    sc["particles"].astype(np.float32).tofile(pfile)
+    cube = os.path.join(scenes.ASSET_DIR, "displacement_r8.bin")
+    res = subprocess.run([exe, lib_path, cube, pfile, "8", "8", "1.0", "48", "48", str(sc["camera"]["position"][2]), str(frames), out],
+                         check=True, capture_output=True, text=True)
+    summary = dict(kv.split("=") for kv in res.stdout.split())
+    return np.fromfile(out, dtype=np.float32).reshape(48, 48, 4), summary
+
+
+def test_python_mirror_frame_structure_over_the_oracle():
+    from oracle_lib import load_oracle
+    check_frame_structure(load_oracle())
+
+
+def test_cpp_mirror_over_the_oracle(tmp_path):
+    from oracle_lib import load_oracle, ORACLE_LIB
+    img, summary = run_cli(build_cli(tmp_path), ORACLE_LIB, tmp_path, frames=5)
+    assert summary["backend"] == "oracle" and summary["fills"] == "3"      # frames 0, 2, 4 (updateInterval 2)
+    sc = scenes.make_scene("cfg1", image=(48, 48))
+    r = make_renderer(load_oracle(), sc)
+    want = r.OnPostRender(sc["particles"], sc["camera"])
+    assert np.array_equal(img, want)
+    assert int(summary["covered"]) == 218 and int(summary["pairs"]) == 457
+
+
+@pytest.mark.gpu
+def test_python_mirror_frame_structure_on_cuda():
+    check_frame_structure(None)
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_on_cuda(tmp_path):
+    img, summary = run_cli(build_cli(tmp_path), vpe_b200.CUDA_LIB_PATH, tmp_path, frames=3)
+    assert summary["backend"] == "cuda" and summary["fills"] == "2"
+    assert int(summary["covered"]) == 218 and int(summary["pairs"]) == 457
+    sc = scenes.make_scene("cfg1", image=(48, 48))
+    r = make_renderer(None, sc)
+    want = r.OnPostRender(sc["particles"], sc["camera"])
+    assert max_rel_err(img, want) <= 1e-6
+    from oracle_lib import load_oracle
+    ref = make_renderer(load_oracle(), sc)
+    assert max_rel_err(img, ref.OnPostRender(sc["particles"], sc["camera"])) <= RTOL
