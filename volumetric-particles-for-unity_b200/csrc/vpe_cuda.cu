@@ -388,18 +388,19 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     CUDA_TRY(c, cudaEventRecord(c->evMarchK0, c->stream));
     if (m.numPixels > 0) {
         const bool legacy = m.wrap || getenv("VPE_MARCH_LEGACY");
-#define VPE_LAUNCH_MARCH(NT)                                                                          \
-    do {                                                                                              \
-        if (partial && skip) k_march<NT, true, false, true><<<grid, block, 0, c->stream>>>(g, m, a);  \
-        else if (partial) k_march<NT, true, false, false><<<grid, block, 0, c->stream>>>(g, m, a);    \
-        else if (skip) k_march<NT, false, false, true><<<grid, block, 0, c->stream>>>(g, m, a);       \
-        else k_march<NT, false, false, false><<<grid, block, 0, c->stream>>>(g, m, a);                \
+        // r == g == b in every texel iff the three ambient components are the same bits (Fill.shader:244)
+        const bool gray = k.ambientColor[0] == k.ambientColor[1] && k.ambientColor[1] == k.ambientColor[2] && !getenv("VPE_MARCH_NO_GRAY");
+#define VPE_LAUNCH_MARCH(NT)                                                                       \
+    do {                                                                                           \
+        if (skip && gray) k_march<NT, false, true, true><<<grid, block, 0, c->stream>>>(g, m, a);  \
+        else if (skip) k_march<NT, false, true, false><<<grid, block, 0, c->stream>>>(g, m, a);    \
+        else if (gray) k_march<NT, false, false, true><<<grid, block, 0, c->stream>>>(g, m, a);    \
+        else k_march<NT, false, false, false><<<grid, block, 0, c->stream>>>(g, m, a);             \
     } while (0)
-        if (footprint) k_march<-1, false, true><<<grid, block, 0, c->stream>>>(g, m, a);
-        else if (legacy) VPE_LAUNCH_MARCH(-1);
+        if (footprint) k_march<-1, true, false, false><<<grid, block, 0, c->stream>>>(g, m, a);
+        else if (legacy) k_march<-1, false, false, false><<<grid, block, 0, c->stream>>>(g, m, a);
         else if (g.N == 32) VPE_LAUNCH_MARCH(32);
         else if (g.N == 64) VPE_LAUNCH_MARCH(64);
-        else if (g.N == 8) VPE_LAUNCH_MARCH(8);
         else VPE_LAUNCH_MARCH(0);
 #undef VPE_LAUNCH_MARCH
     }
