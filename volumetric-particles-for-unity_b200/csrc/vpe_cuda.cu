@@ -172,6 +172,7 @@ void rebuild_grid_params(VpeContext* c) {
         const float cmax = std::max(fabsf(g.center.x), std::max(fabsf(g.center.y), fabsf(g.center.z)));
         g.worldReach = cmax + 0.5f * 1.7320508f * (maxG + 2.0f) * g.sb * 1.01f;
     }
+    g.swz = (g.N % 16 == 0 && !getenv("VPE_NO_SWIZZLE")) ? 8 : 0;
 }
 
 int sync_stream(VpeContext* c) {
@@ -261,15 +262,7 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1) {
     a.occ = c->occCells ? c->dOcc.p : nullptr; a.occCells = c->occCells;
     a.x0 = x0; a.x1 = x1; a.y0 = y0; a.y1 = y1;
     CUDA_TRY(c, cudaEventRecord(c->evFillK0, c->stream));
-    if (getenv("VPE_FILL_LEGACY")) {
-        const int tiles = div_up((long long)g.N * g.N, FILL_THREADS);
-        for (int zz = g.z0; zz < g.z1; zz++) {  // nearest the light first (VPR.cs:505)
-            int count = c->sliceStart[zz + 1] - c->sliceStart[zz];
-            if (count <= 0) continue;           // VPR.cs:511
-            k_fill_slice<<<dim3(count, tiles), FILL_THREADS, 0, c->stream>>>(g, a, zz);
-            c->stats.fillLaunches++;
-        }
-    } else if (c->nCovered > 0) {
+    if (c->nCovered > 0) {
         // one launch: every voxel column of the region walks all slices of the slab
         const int warpTiles = ((g.N + 7) / 8) * ((g.N + 3) / 4);
         k_fill_columns<<<dim3((x1 - x0) * (y1 - y0), div_up(warpTiles, FILLC_THREADS / 32)), FILLC_THREADS, 0, c->stream>>>(
@@ -358,6 +351,7 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     m.numPixels = pixelsDev ? nPixels : cam->width * cam->height;
     m.maxSamplesPerMv = (int)(1.7320508f / m.stepSize) + 2;
     m.wrap = k.numBorderVoxels == 0 ? 1 : 0;
+    m.swz = g.swz;
 
     CUDA_TRY(c, cudaEventRecord(c->evMarch0, c->stream));
     c->marchTimed = false;
@@ -390,18 +384,24 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
         const bool legacy = m.wrap || getenv("VPE_MARCH_LEGACY");
         // r == g == b in every texel iff the three ambient components are the same bits (Fill.shader:244)
         const bool gray = k.ambientColor[0] == k.ambientColor[1] && k.ambientColor[1] == k.ambientColor[2] && !getenv("VPE_MARCH_NO_GRAY");
-#define VPE_LAUNCH_MARCH(NT)                                                                       \
-    do {                                                                                           \
-        if (skip && gray) k_march<NT, false, true, true><<<grid, block, 0, c->stream>>>(g, m, a);  \
-        else if (skip) k_march<NT, false, true, false><<<grid, block, 0, c->stream>>>(g, m, a);    \
-        else if (gray) k_march<NT, false, false, true><<<grid, block, 0, c->stream>>>(g, m, a);    \
-        else k_march<NT, false, false, false><<<grid, block, 0, c->stream>>>(g, m, a);             \
+#define VPE_LAUNCH_MARCH2(NT, SWZ)                                                                      \
+    do {                                                                                                \
+        if (skip && gray) k_march<NT, false, true, true, SWZ><<<grid, block, 0, c->stream>>>(g, m, a);  \
+        else if (skip) k_march<NT, false, true, false, SWZ><<<grid, block, 0, c->stream>>>(g, m, a);    \
+        else if (gray) k_march<NT, false, false, true, SWZ><<<grid, block, 0, c->stream>>>(g, m, a);    \
+        else k_march<NT, false, false, false, SWZ><<<grid, block, 0, c->stream>>>(g, m, a);             \
     } while (0)
-        if (footprint) k_march<-1, true, false, false><<<grid, block, 0, c->stream>>>(g, m, a);
-        else if (legacy) k_march<-1, false, false, false><<<grid, block, 0, c->stream>>>(g, m, a);
+#define VPE_LAUNCH_MARCH(NT)                     \
+    do {                                         \
+        if (m.swz) VPE_LAUNCH_MARCH2(NT, true);  \
+        else VPE_LAUNCH_MARCH2(NT, false);       \
+    } while (0)
+        if (footprint) k_march<-1, true, false, false, false><<<grid, block, 0, c->stream>>>(g, m, a);
+        else if (legacy) k_march<-1, false, false, false, false><<<grid, block, 0, c->stream>>>(g, m, a);
         else if (g.N == 32) VPE_LAUNCH_MARCH(32);
         else if (g.N == 64) VPE_LAUNCH_MARCH(64);
         else VPE_LAUNCH_MARCH(0);
+#undef VPE_LAUNCH_MARCH2
 #undef VPE_LAUNCH_MARCH
     }
     CUDA_TRY(c, cudaEventRecord(c->evMarchK1, c->stream));
@@ -739,7 +739,19 @@ int vpe_read_brick(VpeContext* c, int x, int y, int z, uint16_t* half4, int* cov
     if (brick < 0) return VPE_OK;
     *covered = 1;
     size_t texels = (size_t)c->g.N * c->g.N * c->g.N;
-    if (half4) CUDA_TRY(c, cudaMemcpy(half4, c->dBricks.p + (size_t)brick * texels, texels * sizeof(uint2), cudaMemcpyDeviceToHost));
+    if (half4) {
+        CUDA_TRY(c, cudaMemcpy(half4, c->dBricks.p + (size_t)brick * texels, texels * sizeof(uint2), cudaMemcpyDeviceToHost));
+        if (c->g.swz) {  // undo the storage swizzle of odd rows: the hook returns [slice][row][col]
+            const int N = c->g.N;
+            uint64_t* t = reinterpret_cast<uint64_t*>(half4);
+            for (int z = 0; z < N; z++)
+                for (int y = 1; y < N; y += 2) {
+                    uint64_t* rowp = t + ((size_t)z * N + y) * N;
+                    for (int x = 0; x < N; x++)
+                        if ((x ^ c->g.swz) > x) std::swap(rowp[x], rowp[x ^ c->g.swz]);
+                }
+        }
+    }
     return VPE_OK;
 }
 
