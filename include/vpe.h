@@ -162,6 +162,14 @@ int vpe_march_device(VpeContext* ctx, const VpeCamera* cam, float* rgba_dev, int
 int vpe_fill_prepare(VpeContext* ctx, const VpeParticle* particles, int n,
                      const VpeTransform* emitter, int particlesOnDevice);
 int vpe_fill_region(VpeContext* ctx, int x0, int x1, int y0, int y1);
+/* The same fill split at its only cross-slab dependency, so that slabs scale: vpe_fill_density runs
+ * the particle loop of the whole slab (Fill.shader:155-208: density and ambient-occlusion term of
+ * every voxel; no light involved, every GPU runs it at once), vpe_fill_sweep_region then runs the
+ * light sweep (Fill.shader:211-269) of a metavoxel-column region through the slab's slices, reading
+ * and updating the light sheet like vpe_fill_region. density + sweep(region) == fill_region(region),
+ * bit for bit. Between the two calls the bricks hold an intermediate and must not be marched. */
+int vpe_fill_density(VpeContext* ctx);
+int vpe_fill_sweep_region(VpeContext* ctx, int x0, int x1, int y0, int y1);
 float* vpe_light_sheet_device(VpeContext* ctx);
 /* Slab-local march: two premultiplied RGBA partial images (device, height*width*4 floats each):
  * over = the slab's slices <= zBoundary composited back-to-front (phase 1, VPR.cs:652-681),

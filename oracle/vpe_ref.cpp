@@ -949,6 +949,15 @@ int vpe_fill_region(VpeContext* c, int x0, int x1, int y0, int y1) {
     return VPE_OK;
 }
 
+// The split entry points of the multi-GPU fill. The oracle keeps the reference's fused per-column
+// fragment: the density pass has nothing to do ahead of time, the sweep of a region is the fused fill.
+int vpe_fill_density(VpeContext* c) {
+    if (!c) return VPE_E_INVALID_ARG;
+    if (!c->prepared) return fail(c, VPE_E_NOT_READY, "vpe_fill_prepare has not been called");
+    return VPE_OK;
+}
+int vpe_fill_sweep_region(VpeContext* c, int x0, int x1, int y0, int y1) { return vpe_fill_region(c, x0, x1, y0, y1); }
+
 int vpe_fill(VpeContext* c, const VpeParticle* particles, int n, const VpeTransform* emitter) {
     double t0 = now_ms();
     int rc = vpe_fill_prepare(c, particles, n, emitter, 0);

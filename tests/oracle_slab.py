@@ -31,6 +31,12 @@ class OracleSlabEngine:
     def fill_region(self, x0, x1, y0, y1):
         self.eng.fill_region(x0, x1, y0, y1)
 
+    def fill_density(self):
+        assert self.lib.vpe_fill_density(self.eng._ctx) == 0
+
+    def fill_sweep_region(self, x0, x1, y0, y1):
+        self.eng.fill_sweep_region(x0, x1, y0, y1)
+
     def sheet_tensor(self):
         return self._sheet
 

@@ -40,10 +40,11 @@ def test_two_slab_contexts_on_one_gpu():
     gx = ranks[0].grid[0]
     for e in ranks:
         e.fill_prepare(sc["particles"], sc["emitter"])
+        e.fill_density()
     for (y0, y1) in bands:  # the pipeline of SlabRenderer.fill, with a device copy in place of NCCL
-        ranks[0].fill_region(0, gx, y0, y1)
+        ranks[0].fill_sweep_region(0, gx, y0, y1)
         ranks[1].sheet_tensor()[y0 * n:y1 * n].copy_(ranks[0].sheet_tensor()[y0 * n:y1 * n])
-        ranks[1].fill_region(0, gx, y0, y1)
+        ranks[1].fill_sweep_region(0, gx, y0, y1)
     torch.cuda.synchronize()
     # volume: bit-exact with the single context, each brick on its owner
     cov = 0

@@ -83,6 +83,8 @@ PROTOTYPES = {
     "vpe_march_device": (C.c_int, [_P, C.POINTER(VpeCamera), _P, _P]),
     "vpe_fill_prepare": (C.c_int, [_P, _P, C.c_int, C.POINTER(VpeTransform), C.c_int]),
     "vpe_fill_region": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vpe_fill_density": (C.c_int, [_P]),
+    "vpe_fill_sweep_region": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "vpe_light_sheet_device": (_P, [_P]),
     "vpe_march_partial_device": (C.c_int, [_P, C.POINTER(VpeCamera), _P, _P, _P]),
     "vpe_composite_device": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_int, _P]),

@@ -253,7 +253,9 @@ int fill_prepare_impl(VpeContext* c, const float* particlesDev, int n, const Vpe
     return VPE_OK;
 }
 
-int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1) {
+enum FillPhase { FILL_FUSED, FILL_DENSITY, FILL_SWEEP };
+
+int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1, FillPhase phase = FILL_FUSED) {
     GridParams& g = c->g;
     FillArgs a;
     a.covered = c->dCovered.p; a.sliceStart = c->dSliceStart.p; a.cellStart = c->dCellStart.p; a.pairs = c->dPairs.p;
@@ -265,8 +267,10 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1) {
     if (c->nCovered > 0) {
         // one launch: every voxel column of the region walks all slices of the slab
         const int warpTiles = ((g.N + 7) / 8) * ((g.N + 3) / 4);
-        k_fill_columns<<<dim3((x1 - x0) * (y1 - y0), div_up(warpTiles, FILLC_THREADS / 32)), FILLC_THREADS, 0, c->stream>>>(
-            g, a, c->dBrickOf.p, c->dCubeFp.p);
+        const dim3 grid((x1 - x0) * (y1 - y0), div_up(warpTiles, FILLC_THREADS / 32));
+        if (phase == FILL_FUSED) k_fill_columns<false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p);
+        else if (phase == FILL_DENSITY) k_fill_columns<true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p);
+        else k_sweep_columns<<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p);
         c->stats.fillLaunches++;
     }
     CUDA_TRY(c, cudaGetLastError());
@@ -630,6 +634,21 @@ int vpe_fill_device(VpeContext* c, const VpeParticle* particles_dev, int n, cons
     int rc = vpe_fill_prepare(c, particles_dev, n, emitter, 1);
     if (rc) return rc;
     return fill_region_impl(c, 0, c->g.NX, 0, c->g.NY);
+}
+
+int vpe_fill_density(VpeContext* c) {
+    if (!c) return VPE_E_INVALID_ARG;
+    if (!c->prepared) return fail(c, VPE_E_NOT_READY, "vpe_fill_prepare has not been called");
+    cudaSetDevice(c->device);
+    return fill_region_impl(c, 0, c->g.NX, 0, c->g.NY, FILL_DENSITY);
+}
+
+int vpe_fill_sweep_region(VpeContext* c, int x0, int x1, int y0, int y1) {
+    if (!c) return VPE_E_INVALID_ARG;
+    if (!c->prepared) return fail(c, VPE_E_NOT_READY, "vpe_fill_prepare has not been called");
+    if (x0 < 0 || y0 < 0 || x1 > c->g.NX || y1 > c->g.NY || x0 >= x1 || y0 >= y1) return fail(c, VPE_E_INVALID_ARG, "bad region");
+    cudaSetDevice(c->device);
+    return fill_region_impl(c, x0, x1, y0, y1, FILL_SWEEP);
 }
 
 float* vpe_light_sheet_device(VpeContext* c) { return c ? c->dSheet.p : nullptr; }

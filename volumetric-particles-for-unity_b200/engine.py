@@ -164,6 +164,12 @@ class Engine:
     def fill_region(self, x0, x1, y0, y1):
         self._check(self.lib.vpe_fill_region(self._ctx, x0, x1, y0, y1))
 
+    def fill_density(self):
+        self._check(self.lib.vpe_fill_density(self._ctx))
+
+    def fill_sweep_region(self, x0, x1, y0, y1):
+        self._check(self.lib.vpe_fill_sweep_region(self._ctx, x0, x1, y0, y1))
+
     def march(self, camera, want_samples=True, out=None, samples_out=None):
         c = _camera(camera)
         rgba = out if out is not None else np.empty((c.height, c.width, 4), dtype=np.float32)

@@ -6,10 +6,13 @@ Rank r owns the metavoxel slices z in [r*NZ/R, (r+1)*NZ/R) — slice 0 is neares
 
 Fill (≙ FillMetavoxels, VPR.cs:495-520).  The only dependency between slabs is the light sheet
 (lightPropogationUAV, VPR.cs:266; Fill.shader:224,250): slab r+1 needs the sheet as slab r left it.
-The metavoxel columns are cut into `tiles` bands of rows; for every band, in order, a rank receives
-the band's sheet rows from rank r-1, fills the band through its own slices (vpe_fill_region) and
-sends the rows on to rank r+1.  Bands pipeline through the ranks: after R-1 bands every GPU is busy.
-Per band the message is (rows*N) x (NX*N) fp32 — the exit-plane light sheet of north_star.
+So the fill is split there.  Phase 1 (vpe_fill_density): every rank runs the particle loop of its
+whole slab — density and ambient-occlusion term of every voxel, the dominant cost, no light involved
+— at once.  Phase 2 (vpe_fill_sweep_region): the light sweep, an HBM-bound pass.  The metavoxel
+columns are cut into bands of rows; for every band, in order, a rank receives the band's sheet rows
+from rank r-1, sweeps the band through its own slices and sends the rows on to rank r+1.  Bands
+pipeline through the ranks: after R-1 bands every GPU is busy.  Per band the message is
+(rows*N) x (NX*N) fp32 — the exit-plane light sheet of north_star.
 
 March (≙ RenderMetavoxels, VPR.cs:637-713).  The reference composites metavoxels slice-major:
 slices 0..zB far-to-near with OVER, then zB+1..NZ-1 near-to-far with UNDER (VPR.cs:652-711).  A
@@ -80,26 +83,31 @@ class SlabRenderer:
         gx, gy, gz = e.grid
         n = e.N
         e.fill_prepare(particles, emitter)          # bins into this slab only, clears the sheet to 1
+        if self.world == 1:
+            e.fill_region(0, gx, 0, gy)             # fused: nothing to wait for
+            return
+        e.fill_density()                            # phase 1: the particle loop of the whole slab, no dependency
         sheet = e.sheet_tensor()                    # (NY*N, NX*N) fp32 view of the context's sheet
-        for (y0, y1) in self.bands:
+        for (y0, y1) in self.bands:                 # phase 2: the light sweep, pipelined through the ranks
             rows = sheet[y0 * n:y1 * n]
             if self.rank > 0:
                 d.recv(rows, src=self.rank - 1)     # the sheet as the previous slab left it
                 e.sheet_written(y0, y1)
-            e.fill_region(0, gx, y0, y1)
+            e.fill_sweep_region(0, gx, y0, y1)
             if self.rank < self.world - 1:
                 e.sheet_read(y0, y1)
                 d.send(rows, dst=self.rank + 1)
 
     # -- march ------------------------------------------------------------------------------------
-    def march(self, camera, gather=True):
+    def march(self, camera, gather=True, count_samples=True):
         """Returns (rgba, total_ray_samples): rgba is the full H x W x 4 image on rank 0 when
-        `gather` (None elsewhere), else this rank's band."""
+        `gather` (None elsewhere), else this rank's band. count_samples=False skips the read-back
+        and all-reduce of the sample counter (a host synchronisation) and returns None for it."""
         e, d = self.e, self.dist
         h, w = int(camera["height"]), int(camera["width"])
         per = -(-h // self.world)                    # image rows per owner; the image is padded to R * per rows
         over, under = e.march_partial(camera, per * self.world)   # 2 x (R*per, W, 4), premultiplied; rows >= H stay 0
-        samples = e.last_ray_samples()
+        samples = e.last_ray_samples() if count_samples else None
         if self.world == 1:
             out = e.composite([over, under], h * w).reshape(h, w, 4)
             return out, samples
@@ -112,7 +120,7 @@ class SlabRenderer:
         for s in range(self.world):                  # ascending slab order = ascending z
             parts += [recv_over[s], recv_under[s]]
         band = e.composite(parts, per * w).reshape(per, w, 4)
-        total = e.all_reduce_sum(d, samples)
+        total = e.all_reduce_sum(d, samples) if count_samples else None
         if not gather:
             r0, r1 = image_band(h, self.world, self.rank)
             return band[:r1 - r0], total
@@ -163,6 +171,12 @@ class CudaSlabEngine:
 
     def fill_region(self, x0, x1, y0, y1):
         self.eng.fill_region(x0, x1, y0, y1)
+
+    def fill_density(self):
+        self.eng.fill_density()
+
+    def fill_sweep_region(self, x0, x1, y0, y1):
+        self.eng.fill_sweep_region(x0, x1, y0, y1)
 
     def sheet_tensor(self):
         if self._sheet is None:
@@ -266,13 +280,12 @@ def bench_multi_gpu(args, metric, measured_peak_hbm, ClockSampler):
         ev[i][0].record()
         r.fill(parts_dev, sc["emitter"])
         ev[i][1].record()
-        _, total_samples = r.march(cam, gather=False)   # (the sample-count all-reduce reads back: a sync per step)
+        r.march(cam, gather=False, count_samples=False)
         ev[i][2].record()
-        st = eng.stats()
-        kern_march.append(st["marchKernelMs"])
-        kern_fill.append(st["fillKernelMs"])
     t1.record()
     sync()
+    _, total_samples = r.march(cam, gather=False)        # untimed: the ray-sample count of the frame
+    kern_march.append(eng.stats()["marchKernelMs"])
     clk = clocks.stop()
     total_ms = max_over_ranks(t0.elapsed_time(t1))
     fill_ms = max_over_ranks(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
@@ -291,7 +304,7 @@ def bench_multi_gpu(args, metric, measured_peak_hbm, ClockSampler):
         sync()
         a = time.perf_counter()
         r.fill(parts_host, sc["emitter"])
-        img, _ = r.march(cam, gather=True)
+        img, _ = r.march(cam, gather=True, count_samples=False)
         if rank == 0:
             rgba_host.copy_(img, non_blocking=False)
         sync()
