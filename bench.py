@@ -162,18 +162,27 @@ def cpu_sample(cfg_name, steps, warmup, tile=128):
     }
 
 
+def workload_name(cfg_name, sc):
+    return "%s: %d^3 grid x %d^3 voxels, %d particles, %dx%d, %d steps/metavoxel" % (
+        cfg_name, sc["grid"][0], sc["numVoxels"], sc["particles"].shape[0], sc["camera"]["width"], sc["camera"]["height"],
+        sc["rayMarchSteps"])
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg_name = args.config or "cfg3"
     r = cpu_sample(cfg_name, max(1, args.steps), max(0, args.warmup))
+    from vpe_b200 import scenes
     line = {
         "impl": "reference", "metric": METRIC, "value": r["march_samples_per_s"], "unit": "ray-samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["fill_ms"] + r["march_ms"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg_name + " (bounded sample)", "note": "CPU oracle (C++ restatement of the reference's "
-                   "shader + dispatch math; the reference is HLSL + C#/Unity and cannot run headless)"},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(cfg_name, scenes.make_scene(cfg_name)),
+                   "sample": "each step is a bounded sample of the workload, see cpu_baseline.sample",
+                   "note": "CPU oracle (C++ restatement of the reference's shader + dispatch math, OpenMP over all host cores); "
+                           "the reference itself is HLSL + C#/Unity and cannot run headless"},
         "fill": {"value": r["fill_voxels_per_s"], "unit": "voxels/s", "ms": r["fill_ms"]},
         "march": {"value": r["march_samples_per_s"], "unit": "ray-samples/s", "ms": r["march_ms"]},
         "cpu_baseline": {"value": r["march_samples_per_s"], "unit": "ray-samples/s", "cores": r["cores"], "kind": "port",
@@ -285,10 +294,11 @@ def run_cuda(args):
                 "traffic": recorded_traffic("k_march"), "peak_source": peak_src, "algorithmic_bytes": march_bytes,
                 "kernel_ms": mk, "bytes_per_ray_sample": march_bytes / max(samples, 1),
                 "distinct_texels": uniq, "note": "compulsory read set = 8 B x distinct texels in the union of all samples' "
-                "trilinear footprints + 16 B x pixels (SURVEY 8d); the kernel is issue-bound, see DESIGN.md"}
+                "trilinear footprints + 16 B x pixels (SURVEY 8d); the kernel is bound by L1 wavefronts / issue, not HBM (DESIGN.md 5.3); "
+                "traffic = dram bytes of the committed ncu capture (below the compulsory set: zero-density cells are skipped)"}
     fach = fill_bytes / (fk * 1e-3) / 1e9
-    roof_fill = {"kernel": "k_fill_slice", "bound": "hbm", "achieved": fach, "peak": peak, "unit": "GB/s", "frac": fach / peak,
-                 "traffic": recorded_traffic("k_fill_slice"), "algorithmic_bytes": fill_bytes, "kernel_ms": fk,
+    roof_fill = {"kernel": "k_fill_columns", "bound": "hbm", "achieved": fach, "peak": peak, "unit": "GB/s", "frac": fach / peak,
+                 "traffic": recorded_traffic("k_fill_columns"), "algorithmic_bytes": fill_bytes, "kernel_ms": fk,
                  "bytes_per_voxel": 8.0 + 8.0 / N}
 
     cpu = None
@@ -299,10 +309,9 @@ def run_cuda(args):
 
     line = {
         "metric": METRIC, "value": samples / (march_ms * 1e-3), "unit": "ray-samples/s", "n_gpus": 1, "steps": K,
-        "warmup": max(3, args.warmup), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(3, args.warmup), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %d^3 grid x %d^3 voxels, %d particles, %dx%d, %d steps/metavoxel" % (
-            cfg_name, eng.grid[0], N, n, W, H, sc["rayMarchSteps"]),
+        "config": {"workload": workload_name(cfg_name, sc),
             "cache": "inputs larger than L2 (brick pool %.2f GB vs 126 MB L2); no flush between iterations" % (st["brickPoolBytes"] / 1e9),
             "early_out_transmittance": args.early_out, "covered_metavoxels": st["numMetavoxelsCovered"],
             "particle_metavoxel_pairs": st["numParticlePairs"]},

@@ -326,7 +326,7 @@ def bench_multi_gpu(args, metric, measured_peak_hbm, ClockSampler):
         "warmup": warm, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %d^3 grid x %d^3 voxels, %d particles, %dx%d, %d steps/metavoxel" % (
-            cfg_name, eng.grid[0], N, n, W, H, sc["rayMarchSteps"]),
+            cfg_name, eng.grid[0], N, n, W, H, sc["rayMarchSteps"]),  # same string as bench.workload_name
             "parallelism": "light-axis slabs x%d (fill: sheet rows over NCCL send/recv in %d bands; march: slab-local + "
                            "all-to-all ordered compositing)" % (world, len(r.bands)),
             "cache": "inputs larger than L2 (brick pools %.2f GB in total); no flush between iterations" % (pool / 1e9),
