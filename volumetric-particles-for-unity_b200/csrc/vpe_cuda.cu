@@ -388,12 +388,21 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
         const bool legacy = m.wrap || getenv("VPE_MARCH_LEGACY");
         // r == g == b in every texel iff the three ambient components are the same bits (Fill.shader:244)
         const bool gray = k.ambientColor[0] == k.ambientColor[1] && k.ambientColor[1] == k.ambientColor[2] && !getenv("VPE_MARCH_NO_GRAY");
-#define VPE_LAUNCH_MARCH2(NT, SWZ)                                                                      \
+        // k_march_merged trades divergence (26.6 instead of 22.6 active lanes) for L1 bank conflicts (lanes in
+        // different bricks): 9.2 vs 8.9 ms on cfg3 with 8-byte texels (profiles/). Opt-in until the texel fetch is cheaper.
+        const bool merged = getenv("VPE_MARCH_MERGED") != nullptr;
+#define VPE_LAUNCH_MARCH3(KERNEL, ...)                                                                  \
     do {                                                                                                \
-        if (skip && gray) k_march<NT, false, true, true, SWZ><<<grid, block, 0, c->stream>>>(g, m, a);  \
-        else if (skip) k_march<NT, false, true, false, SWZ><<<grid, block, 0, c->stream>>>(g, m, a);    \
-        else if (gray) k_march<NT, false, false, true, SWZ><<<grid, block, 0, c->stream>>>(g, m, a);    \
-        else k_march<NT, false, false, false, SWZ><<<grid, block, 0, c->stream>>>(g, m, a);             \
+        if (skip && gray) KERNEL<__VA_ARGS__, true, true, SWZ_><<<grid, block, 0, c->stream>>>(g, m, a); \
+        else if (skip) KERNEL<__VA_ARGS__, true, false, SWZ_><<<grid, block, 0, c->stream>>>(g, m, a);   \
+        else if (gray) KERNEL<__VA_ARGS__, false, true, SWZ_><<<grid, block, 0, c->stream>>>(g, m, a);   \
+        else KERNEL<__VA_ARGS__, false, false, SWZ_><<<grid, block, 0, c->stream>>>(g, m, a);            \
+    } while (0)
+#define VPE_LAUNCH_MARCH2(NT, SWZ)                           \
+    do {                                                     \
+        constexpr bool SWZ_ = SWZ;                           \
+        if (merged) VPE_LAUNCH_MARCH3(k_march_merged, NT);   \
+        else VPE_LAUNCH_MARCH3(k_march, NT, false);          \
     } while (0)
 #define VPE_LAUNCH_MARCH(NT)                     \
     do {                                         \
@@ -406,6 +415,7 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
         else if (g.N == 64) VPE_LAUNCH_MARCH(64);
         else VPE_LAUNCH_MARCH(0);
 #undef VPE_LAUNCH_MARCH2
+#undef VPE_LAUNCH_MARCH3
 #undef VPE_LAUNCH_MARCH
     }
     CUDA_TRY(c, cudaEventRecord(c->evMarchK1, c->stream));
