@@ -29,14 +29,15 @@ struct GridParams {
     float depthB, depthRcpA;    // Fill.shader:217-218: b, rcp(a)
     int cubeEdge;
     float worldReach;           // bound on |coordinate| of any voxel centre of the grid (pre-test error band)
-    int swz;                    // brick rows with odd y store texel x at x ^ swz (8 when N % 16 == 0, else 0)
+    int rowStride;              // texels between stored brick rows: N + 8 when N % 16 == 0 (bank spread), else N
+    int gray;                   // ambient r == g == b (same bits): bricks hold z-paired (r,density) texels
 };
 
-// Texel (x,y,z) of a brick. Rows are 8-byte texels, x fastest; odd rows are XOR-swizzled by half a
-// 128-byte line so that vertically adjacent rows fall into different L1 banks (the march's warp tile
-// reads 4 rows at the same x in one load instruction).
-VPE_HD size_t brick_texel_index(int N, int swz, int x, int y, int z) {
-    return ((size_t)z * N + y) * N + (size_t)(x ^ ((y & 1) ? swz : 0));
+// Texel (x,y,z) of a brick. Texels are 8 bytes, x fastest; rows are rowStride texels apart: padded by
+// half a 128-byte line when N % 16 == 0 so that vertically adjacent rows fall into different L1 banks
+// (the march's warp tile reads 4 rows at about the same x in one load instruction).
+VPE_HD size_t brick_texel_index(int N, int rowStride, int x, int y, int z) {
+    return ((size_t)z * N + y) * rowStride + (size_t)x;
 }
 
 // world-space centre of metavoxel (x,y,z), VPR.cs:388-390
@@ -83,7 +84,8 @@ struct MarchParams {
     int maxSamplesPerMv;         // hang guard: (int)(sqrt(3)/stepSize) + 2
     int wrap;                    // border == 0: repeat addressing can trigger (VPR.cs:770)
     int tileLog2W;               // warp pixel tile = 2^tileLog2W x (32 >> tileLog2W)
-    int swz;                     // = GridParams::swz
+    int rowStride;               // = GridParams::rowStride
+    int gray;                    // layout of the bricks being marched (GridParams::gray at fill time)
 };
 
 }  // namespace vpe

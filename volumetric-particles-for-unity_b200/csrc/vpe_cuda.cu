@@ -81,6 +81,7 @@ struct VpeContext {
     DevBuf<unsigned long long> dTotalSamples;
     DevBuf<const float4*> dParts;
     bool depthSet = false;
+    bool bricksGray = false;         // layout of the bricks of the last fill (GridParams::gray at that time)
     int cubeEdge = 0;
     // pinned host staging
     int* hCounts = nullptr;  // [NZ + 3]: sliceStart[NZ+1], totals[2]
@@ -172,7 +173,10 @@ void rebuild_grid_params(VpeContext* c) {
         const float cmax = std::max(fabsf(g.center.x), std::max(fabsf(g.center.y), fabsf(g.center.z)));
         g.worldReach = cmax + 0.5f * 1.7320508f * (maxG + 2.0f) * g.sb * 1.01f;
     }
-    g.swz = (g.N % 16 == 0 && !getenv("VPE_NO_SWIZZLE")) ? 8 : 0;
+    g.rowStride = g.N + ((g.N % 16 == 0 && !getenv("VPE_NO_ROWPAD")) ? ROW_PAD : 0);
+    // r == g == b in every texel iff the three ambient components are the same bits (Fill.shader:244)
+    g.gray = (memcmp(&k.ambientColor[0], &k.ambientColor[1], sizeof(float)) == 0 &&
+              memcmp(&k.ambientColor[1], &k.ambientColor[2], sizeof(float)) == 0 && !getenv("VPE_NO_GRAY")) ? 1 : 0;
 }
 
 int sync_stream(VpeContext* c) {
@@ -221,7 +225,7 @@ int fill_prepare_impl(VpeContext* c, const float* particlesDev, int n, const Vpe
         c->stats.fillLaunches += 2;
     }
     // brick pool: one N^3 half4 brick per covered metavoxel (≙ lazily created mvFillTextures, VPR.cs:565-566)
-    const size_t brickTexels = (size_t)g.N * g.N * g.N;
+    const size_t brickTexels = (size_t)g.N * g.N * g.rowStride;  // stored size (rows padded), DESIGN.md §4
     size_t want = (size_t)c->nCovered;
     if (want * brickTexels > c->dBricks.cap) {
         size_t padded = std::min((size_t)cells, want + want / 16 + 8);
@@ -249,7 +253,7 @@ int fill_prepare_impl(VpeContext* c, const float* particlesDev, int n, const Vpe
     c->stats.numParticles = n;
     c->stats.numMetavoxelsCovered = c->nCovered;
     c->stats.numParticlePairs = c->nPairs;
-    c->stats.voxelsFilled = (int64_t)c->nCovered * (int64_t)brickTexels;
+    c->stats.voxelsFilled = (int64_t)c->nCovered * (int64_t)g.N * g.N * g.N;
     return VPE_OK;
 }
 
@@ -264,13 +268,16 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1, FillPhase ph
     a.occ = c->occCells ? c->dOcc.p : nullptr; a.occCells = c->occCells;
     a.x0 = x0; a.x1 = x1; a.y0 = y0; a.y1 = y1;
     CUDA_TRY(c, cudaEventRecord(c->evFillK0, c->stream));
+    if (phase != FILL_DENSITY) c->bricksGray = g.gray != 0;
     if (c->nCovered > 0) {
         // one launch: every voxel column of the region walks all slices of the slab
         const int warpTiles = ((g.N + 7) / 8) * ((g.N + 3) / 4);
         const dim3 grid((x1 - x0) * (y1 - y0), div_up(warpTiles, FILLC_THREADS / 32));
-        if (phase == FILL_FUSED) k_fill_columns<false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p);
-        else if (phase == FILL_DENSITY) k_fill_columns<true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p);
-        else k_sweep_columns<<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p);
+        if (phase == FILL_FUSED && g.gray) k_fill_columns<false, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p);
+        else if (phase == FILL_FUSED) k_fill_columns<false, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p);
+        else if (phase == FILL_DENSITY) k_fill_columns<true, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p);
+        else if (g.gray) k_sweep_columns<true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p);
+        else k_sweep_columns<false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p);
         c->stats.fillLaunches++;
     }
     CUDA_TRY(c, cudaGetLastError());
@@ -355,7 +362,8 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     m.numPixels = pixelsDev ? nPixels : cam->width * cam->height;
     m.maxSamplesPerMv = (int)(1.7320508f / m.stepSize) + 2;
     m.wrap = k.numBorderVoxels == 0 ? 1 : 0;
-    m.swz = g.swz;
+    m.rowStride = g.rowStride;
+    m.gray = c->bricksGray ? 1 : 0;
 
     CUDA_TRY(c, cudaEventRecord(c->evMarch0, c->stream));
     c->marchTimed = false;
@@ -386,27 +394,26 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     CUDA_TRY(c, cudaEventRecord(c->evMarchK0, c->stream));
     if (m.numPixels > 0) {
         const bool legacy = m.wrap || getenv("VPE_MARCH_LEGACY");
-        // r == g == b in every texel iff the three ambient components are the same bits (Fill.shader:244)
-        const bool gray = k.ambientColor[0] == k.ambientColor[1] && k.ambientColor[1] == k.ambientColor[2] && !getenv("VPE_MARCH_NO_GRAY");
+        const bool gray = c->bricksGray;  // the layout the fill wrote (z-paired grey texels or half4)
         // k_march_merged trades divergence (26.6 instead of 22.6 active lanes) for L1 bank conflicts (lanes in
         // different bricks): 9.2 vs 8.9 ms on cfg3 with 8-byte texels (profiles/). Opt-in until the texel fetch is cheaper.
         const bool merged = getenv("VPE_MARCH_MERGED") != nullptr;
 #define VPE_LAUNCH_MARCH3(KERNEL, ...)                                                                  \
     do {                                                                                                \
-        if (skip && gray) KERNEL<__VA_ARGS__, true, true, SWZ_><<<grid, block, 0, c->stream>>>(g, m, a); \
-        else if (skip) KERNEL<__VA_ARGS__, true, false, SWZ_><<<grid, block, 0, c->stream>>>(g, m, a);   \
-        else if (gray) KERNEL<__VA_ARGS__, false, true, SWZ_><<<grid, block, 0, c->stream>>>(g, m, a);   \
-        else KERNEL<__VA_ARGS__, false, false, SWZ_><<<grid, block, 0, c->stream>>>(g, m, a);            \
+        if (skip && gray) KERNEL<__VA_ARGS__, true, true, PAD_><<<grid, block, 0, c->stream>>>(g, m, a); \
+        else if (skip) KERNEL<__VA_ARGS__, true, false, PAD_><<<grid, block, 0, c->stream>>>(g, m, a);   \
+        else if (gray) KERNEL<__VA_ARGS__, false, true, PAD_><<<grid, block, 0, c->stream>>>(g, m, a);   \
+        else KERNEL<__VA_ARGS__, false, false, PAD_><<<grid, block, 0, c->stream>>>(g, m, a);            \
     } while (0)
-#define VPE_LAUNCH_MARCH2(NT, SWZ)                           \
+#define VPE_LAUNCH_MARCH2(NT, PAD)                           \
     do {                                                     \
-        constexpr bool SWZ_ = SWZ;                           \
+        constexpr bool PAD_ = PAD;                           \
         if (merged) VPE_LAUNCH_MARCH3(k_march_merged, NT);   \
         else VPE_LAUNCH_MARCH3(k_march, NT, false);          \
     } while (0)
 #define VPE_LAUNCH_MARCH(NT)                     \
     do {                                         \
-        if (m.swz) VPE_LAUNCH_MARCH2(NT, true);  \
+        if (m.rowStride != g.N) VPE_LAUNCH_MARCH2(NT, true);  \
         else VPE_LAUNCH_MARCH2(NT, false);       \
     } while (0)
         if (footprint) k_march<-1, true, false, false, false><<<grid, block, 0, c->stream>>>(g, m, a);
@@ -769,16 +776,15 @@ int vpe_read_brick(VpeContext* c, int x, int y, int z, uint16_t* half4, int* cov
     *covered = 1;
     size_t texels = (size_t)c->g.N * c->g.N * c->g.N;
     if (half4) {
-        CUDA_TRY(c, cudaMemcpy(half4, c->dBricks.p + (size_t)brick * texels, texels * sizeof(uint2), cudaMemcpyDeviceToHost));
-        if (c->g.swz) {  // undo the storage swizzle of odd rows: the hook returns [slice][row][col]
-            const int N = c->g.N;
-            uint64_t* t = reinterpret_cast<uint64_t*>(half4);
-            for (int z = 0; z < N; z++)
-                for (int y = 1; y < N; y += 2) {
-                    uint64_t* rowp = t + ((size_t)z * N + y) * N;
-                    for (int x = 0; x < N; x++)
-                        if ((x ^ c->g.swz) > x) std::swap(rowp[x], rowp[x ^ c->g.swz]);
-                }
+        // the hook returns [slice][row][col] half4: drop the row padding
+        const int N = c->g.N, RS = c->g.rowStride;
+        CUDA_TRY(c, cudaMemcpy2D(half4, (size_t)N * sizeof(uint2), c->dBricks.p + (size_t)brick * N * N * RS, (size_t)RS * sizeof(uint2),
+                                 (size_t)N * sizeof(uint2), (size_t)N * N, cudaMemcpyDeviceToHost));
+        if (c->bricksGray) {  // z-paired grey texel -> the half4 (r, r, r, density) it stands for
+            for (size_t i = 0; i < texels; i++) {
+                const uint16_t r = half4[4 * i], d = half4[4 * i + 1];
+                half4[4 * i + 1] = r; half4[4 * i + 2] = r; half4[4 * i + 3] = d;
+            }
         }
     }
     return VPE_OK;
