@@ -171,6 +171,20 @@ int vpe_fill_region(VpeContext* ctx, int x0, int x1, int y0, int y1);
 int vpe_fill_density(VpeContext* ctx);
 int vpe_fill_sweep_region(VpeContext* ctx, int x0, int x1, int y0, int y1);
 float* vpe_light_sheet_device(VpeContext* ctx);
+/* The same sweep with the hand-over of the sheet between neighbouring slabs inside the kernel, over
+ * NVLink peer memory (CUDA library only): every rank owns a link buffer (inbox for the sheet values of
+ * the slab nearer the light + per-block flags). vpe_sheet_link_create allocates it and returns a
+ * 64-byte CUDA IPC handle for other processes and/or the device pointer for contexts of this process;
+ * vpe_sheet_link_connect maps the neighbours' buffers (NULL = no neighbour on that side; handlesAreIpc:
+ * the arguments point to IPC handles, else to device pointers as returned in *devPtr);
+ * vpe_fill_sweep_linked sweeps all metavoxel columns: each block of voxel columns waits for its values
+ * from upstream, sweeps the slab, stores its exit values into the downstream inbox and raises the flag.
+ * All ranks must call it once per fill, after vpe_fill_density. Result: identical to the other paths,
+ * bit for bit. vpe_sheet_link_status reports waits that gave up (a peer that never arrived). */
+int vpe_sheet_link_create(VpeContext* ctx, void* ipcHandle64, void** devPtr);
+int vpe_sheet_link_connect(VpeContext* ctx, const void* upstream, const void* downstream, int handlesAreIpc);
+int vpe_fill_sweep_linked(VpeContext* ctx);
+int vpe_sheet_link_status(VpeContext* ctx, int* timeouts);
 /* Slab-local march: two premultiplied RGBA partial images (device, height*width*4 floats each):
  * over = the slab's slices <= zBoundary composited back-to-front (phase 1, VPR.cs:652-681),
  * under = its slices > zBoundary composited front-to-back (phase 2, VPR.cs:688-711). */

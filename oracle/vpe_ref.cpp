@@ -1021,6 +1021,10 @@ int vpe_set_stream(VpeContext* c, void*) { return fail(c, VPE_E_UNSUPPORTED, "or
 int vpe_fill_device(VpeContext* c, const VpeParticle*, int, const VpeTransform*) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
 int vpe_march_device(VpeContext* c, const VpeCamera*, float*, int32_t*) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
 float* vpe_light_sheet_device(VpeContext*) { return nullptr; }
+int vpe_sheet_link_create(VpeContext* c, void*, void**) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
+int vpe_sheet_link_connect(VpeContext* c, const void*, const void*, int) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
+int vpe_fill_sweep_linked(VpeContext* c) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
+int vpe_sheet_link_status(VpeContext* c, int*) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
 int vpe_march_partial_device(VpeContext* c, const VpeCamera*, float*, float*, int32_t*) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
 int vpe_composite_device(VpeContext* c, const float* const*, int, int, float*) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
 

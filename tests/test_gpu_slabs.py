@@ -75,6 +75,62 @@ def test_two_slab_contexts_on_one_gpu():
     assert max_rel_err(out, img_ref) <= RTOL
 
 
+def test_linked_sweep_two_contexts_on_one_gpu():
+    """vpe_fill_sweep_linked: the sweep kernel itself hands the sheet to the next slab (peer stores + a flag
+    per block of voxel columns). Two contexts of one process share the GPU here; the upstream kernel is
+    launched first. Three fills in a row exercise the epoch and acknowledge flags. Result: bit-identical
+    to the single-context fill."""
+    import torch
+    sc = _scene()
+    one = vpe_b200.engine_for_scene(None, sc)
+    scenes.apply_scene(one, sc)
+    one.fill(sc["particles"], sc["emitter"])
+    ranks = [slabs.CudaSlabEngine(sc, r, 2, 0) for r in range(2)]
+    ptrs = [e.eng.sheet_link_create()[1] for e in ranks]
+    ranks[0].eng.sheet_link_connect(None, ptrs[1])
+    ranks[1].eng.sheet_link_connect(ptrs[0], None)
+    gx, gy, gz = ranks[0].grid
+    for it in range(3):
+        for e in ranks:
+            e.fill_prepare(sc["particles"], sc["emitter"])
+            e.fill_density()
+        torch.cuda.synchronize()
+        for e in ranks:  # upstream first: on one GPU the downstream kernel must not occupy the SMs alone
+            e.fill_sweep_linked()
+            if it == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        assert ranks[0].eng.sheet_link_timeouts() == 0 and ranks[1].eng.sheet_link_timeouts() == 0
+        assert np.array_equal(ranks[1].eng.read_light_sheet(), one.read_light_sheet())
+    cov = 0
+    for z in range(gz):
+        owner = ranks[0] if z < ranks[0].slab[1] else ranks[1]
+        for y in range(gy):
+            for x in range(gx):
+                a, b = one.read_brick(x, y, z), owner.eng.read_brick(x, y, z)
+                assert (a is None) == (b is None)
+                if a is not None:
+                    cov += 1
+                    assert np.array_equal(a, b)
+    assert cov == one.stats()["numMetavoxelsCovered"]
+
+
+def test_linked_sweep_reports_a_missing_peer(monkeypatch):
+    """A downstream rank whose upstream never arrives gives up after the spin limit and says so; it does
+    not hang the GPU."""
+    import torch
+    monkeypatch.setenv("VPE_LINK_SPIN_MS", "20")
+    sc = _scene()
+    ranks = [slabs.CudaSlabEngine(sc, r, 2, 0) for r in range(2)]
+    ptrs = [e.eng.sheet_link_create()[1] for e in ranks]
+    ranks[1].eng.sheet_link_connect(ptrs[0], None)
+    ranks[1].fill_prepare(sc["particles"], sc["emitter"])
+    ranks[1].fill_density()
+    ranks[1].fill_sweep_linked()
+    torch.cuda.synchronize()
+    assert ranks[1].eng.sheet_link_timeouts() > 0
+
+
 def _nccl_worker(rank, world, port, out_dir):
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
@@ -90,11 +146,23 @@ def _nccl_worker(rank, world, port, out_dir):
     try:
         sc = _scene()
         eng = slabs.CudaSlabEngine(sc, rank, world, rank)
-        r = slabs.SlabRenderer(eng, dist, fill_bands=4)
+        r = slabs.SlabRenderer(eng, dist, fill_bands=4)   # NCCL send/recv band pipeline
         r.fill(sc["particles"], sc["emitter"])
         img, total = r.march(sc["camera"])
         torch.cuda.synchronize()
+        sheet_nccl = eng.eng.read_light_sheet()
+        # the same over the sheet link (peer memory, CUDA IPC between the two processes), twice
+        eng2 = slabs.CudaSlabEngine(sc, rank, world, rank)
+        r2 = slabs.SlabRenderer(eng2, dist)
+        assert r2.linked
+        for _ in range(2):
+            r2.fill(sc["particles"], sc["emitter"])
+        img2, total2 = r2.march(sc["camera"])
+        torch.cuda.synchronize()
+        assert eng2.eng.sheet_link_timeouts() == 0
+        assert np.array_equal(eng2.eng.read_light_sheet(), sheet_nccl)
         if rank == 0:
+            assert total2 == total and np.array_equal(img2.cpu().numpy(), img.cpu().numpy())
             np.savez(os.path.join(out_dir, "nccl.npz"), img=img.cpu().numpy(), total=np.int64(total))
     finally:
         dist.destroy_process_group()

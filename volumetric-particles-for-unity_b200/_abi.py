@@ -86,6 +86,10 @@ PROTOTYPES = {
     "vpe_fill_density": (C.c_int, [_P]),
     "vpe_fill_sweep_region": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "vpe_light_sheet_device": (_P, [_P]),
+    "vpe_sheet_link_create": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "vpe_sheet_link_connect": (C.c_int, [_P, _P, _P, C.c_int]),
+    "vpe_fill_sweep_linked": (C.c_int, [_P]),
+    "vpe_sheet_link_status": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "vpe_march_partial_device": (C.c_int, [_P, C.POINTER(VpeCamera), _P, _P, _P]),
     "vpe_composite_device": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_int, _P]),
     "vpe_march_footprint": (C.c_int, [_P, C.POINTER(VpeCamera), C.POINTER(C.c_int64)]),

@@ -80,6 +80,14 @@ struct VpeContext {
     DevBuf<float4> dImage, dImage2;
     DevBuf<unsigned long long> dTotalSamples;
     DevBuf<const float4*> dParts;
+    // sheet link (multi-GPU sweep over peer memory): own buffer [inbox | flagIn | ackIn | timeouts] and the
+    // neighbours' buffers mapped into this process
+    void* linkOwn = nullptr;
+    void* linkUp = nullptr;
+    void* linkDown = nullptr;
+    bool linkUpIpc = false, linkDownIpc = false;
+    int linkBlocks = 0;
+    unsigned linkEpoch = 0;
     bool depthSet = false;
     bool bricksGray = false;         // layout of the bricks of the last fill (GridParams::gray at that time)
     int cubeEdge = 0;
@@ -257,7 +265,24 @@ int fill_prepare_impl(VpeContext* c, const float* particlesDev, int n, const Vpe
     return VPE_OK;
 }
 
-enum FillPhase { FILL_FUSED, FILL_DENSITY, FILL_SWEEP };
+enum FillPhase { FILL_FUSED, FILL_DENSITY, FILL_SWEEP, FILL_SWEEP_LINKED };
+
+// Layout of a sheet link buffer; identical on every rank (same grid and voxel count).
+struct LinkLayout {
+    size_t sheetN, flagOff, ackOff, timeoutOff, bytes;
+    int blocks;
+};
+LinkLayout link_layout(const GridParams& g) {
+    LinkLayout l;
+    const int warpTiles = ((g.N + 7) / 8) * ((g.N + 3) / 4);
+    l.blocks = g.NX * g.NY * ((warpTiles + FILLC_THREADS / 32 - 1) / (FILLC_THREADS / 32));
+    l.sheetN = (size_t)g.NX * g.N * g.NY * g.N;
+    l.flagOff = (l.sheetN * sizeof(float) + 255) / 256 * 256;
+    l.ackOff = l.flagOff + (size_t)l.blocks * sizeof(unsigned);
+    l.timeoutOff = l.ackOff + (size_t)l.blocks * sizeof(unsigned);
+    l.bytes = l.timeoutOff + 256;
+    return l;
+}
 
 int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1, FillPhase phase = FILL_FUSED) {
     GridParams& g = c->g;
@@ -269,15 +294,38 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1, FillPhase ph
     a.x0 = x0; a.x1 = x1; a.y0 = y0; a.y1 = y1;
     CUDA_TRY(c, cudaEventRecord(c->evFillK0, c->stream));
     if (phase != FILL_DENSITY) c->bricksGray = g.gray != 0;
-    if (c->nCovered > 0) {
+    if (c->nCovered > 0 || phase == FILL_SWEEP_LINKED) {  // a linked sweep always runs: its flags must flow
         // one launch: every voxel column of the region walks all slices of the slab
         const int warpTiles = ((g.N + 7) / 8) * ((g.N + 3) / 4);
         const dim3 grid((x1 - x0) * (y1 - y0), div_up(warpTiles, FILLC_THREADS / 32));
         if (phase == FILL_FUSED && g.gray) k_fill_columns<false, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p);
         else if (phase == FILL_FUSED) k_fill_columns<false, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p);
         else if (phase == FILL_DENSITY) k_fill_columns<true, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p);
-        else if (g.gray) k_sweep_columns<true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p);
-        else k_sweep_columns<false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p);
+        else {
+            SheetLink link;
+            memset(&link, 0, sizeof(link));
+            if (phase == FILL_SWEEP_LINKED) {
+                const LinkLayout l = link_layout(g);
+                char* own = static_cast<char*>(c->linkOwn);
+                link.inbox = reinterpret_cast<const float*>(own);
+                link.flagIn = reinterpret_cast<const unsigned*>(own + l.flagOff);
+                link.ackIn = reinterpret_cast<const unsigned*>(own + l.ackOff);
+                link.timeouts = reinterpret_cast<unsigned*>(own + l.timeoutOff);
+                link.hasUp = c->linkUp != nullptr;
+                link.hasDown = c->linkDown != nullptr;
+                if (link.hasUp) link.upAck = reinterpret_cast<unsigned*>(static_cast<char*>(c->linkUp) + l.ackOff);
+                if (link.hasDown) {
+                    link.downInbox = reinterpret_cast<float*>(c->linkDown);
+                    link.downFlag = reinterpret_cast<unsigned*>(static_cast<char*>(c->linkDown) + l.flagOff);
+                }
+                link.epoch = ++c->linkEpoch;
+                const char* ms = getenv("VPE_LINK_SPIN_MS");
+                link.spinLimit = (long long)(ms ? atof(ms) : 2000.0) * 2000000ll;  // ~2 GHz ticks
+                if (g.gray) k_sweep_columns<true, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
+                else k_sweep_columns<false, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
+            } else if (g.gray) k_sweep_columns<true, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
+            else k_sweep_columns<false, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
+        }
         c->stats.fillLaunches++;
     }
     CUDA_TRY(c, cudaGetLastError());
@@ -525,6 +573,9 @@ int vpe_destroy(VpeContext* c) {
     c->dCube.release(); c->dCubeFp.release(); c->dDepth.release(); c->dSheet.release(); c->dBricks.release(); c->dOcc.release(); c->dMvCam.release();
     c->dRank.release(); c->dPixels.release(); c->dSamples.release(); c->dImage.release(); c->dImage2.release();
     c->dTotalSamples.release(); c->dParts.release();
+    if (c->linkUp && c->linkUpIpc) cudaIpcCloseMemHandle(c->linkUp);
+    if (c->linkDown && c->linkDownIpc) cudaIpcCloseMemHandle(c->linkDown);
+    if (c->linkOwn) cudaFree(c->linkOwn);
     if (c->hCounts) cudaFreeHost(c->hCounts);
     if (c->hTotalSamples) cudaFreeHost(c->hTotalSamples);
     if (c->evFill0) cudaEventDestroy(c->evFill0);
@@ -669,6 +720,90 @@ int vpe_fill_sweep_region(VpeContext* c, int x0, int x1, int y0, int y1) {
 }
 
 float* vpe_light_sheet_device(VpeContext* c) { return c ? c->dSheet.p : nullptr; }
+
+int vpe_sheet_link_create(VpeContext* c, void* ipcHandle64, void** devPtr) {
+    if (!c) return VPE_E_INVALID_ARG;
+    cudaSetDevice(c->device);
+    const LinkLayout l = link_layout(c->g);
+    if (!c->linkOwn) {
+        CUDA_TRY(c, cudaMalloc(&c->linkOwn, l.bytes));
+        CUDA_TRY(c, cudaMemset(c->linkOwn, 0, l.bytes));
+        c->linkBlocks = l.blocks;
+        c->linkEpoch = 0;
+    }
+    if (ipcHandle64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+        cudaIpcMemHandle_t h;
+        CUDA_TRY(c, cudaIpcGetMemHandle(&h, c->linkOwn));
+        memcpy(ipcHandle64, &h, sizeof(h));
+    }
+    if (devPtr) *devPtr = c->linkOwn;
+    return VPE_OK;
+}
+
+namespace {
+int link_unmap(VpeContext* c, void*& p, bool& ipc) {
+    if (p && ipc) cudaIpcCloseMemHandle(p);
+    p = nullptr;
+    ipc = false;
+    (void)c;
+    return VPE_OK;
+}
+int link_map(VpeContext* c, const void* src, int isIpc, void*& out, bool& outIpc) {
+    if (!src) return VPE_OK;
+    if (isIpc) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, src, sizeof(h));
+        CUDA_TRY(c, cudaIpcOpenMemHandle(&out, h, cudaIpcMemLazyEnablePeerAccess));
+        outIpc = true;
+    } else {
+        void* p = *static_cast<void* const*>(src);
+        cudaPointerAttributes at;
+        CUDA_TRY(c, cudaPointerGetAttributes(&at, p));
+        if (at.type != cudaMemoryTypeDevice) return fail(c, VPE_E_INVALID_ARG, "sheet link: not a device pointer");
+        if (at.device != c->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else CUDA_TRY(c, e);
+        }
+        out = p;
+        outIpc = false;
+    }
+    return VPE_OK;
+}
+}  // namespace
+
+int vpe_sheet_link_connect(VpeContext* c, const void* upstream, const void* downstream, int handlesAreIpc) {
+    if (!c) return VPE_E_INVALID_ARG;
+    if (!c->linkOwn) return fail(c, VPE_E_NOT_READY, "vpe_sheet_link_create has not been called");
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    link_unmap(c, c->linkUp, c->linkUpIpc);
+    link_unmap(c, c->linkDown, c->linkDownIpc);
+    int rc = link_map(c, upstream, handlesAreIpc, c->linkUp, c->linkUpIpc);
+    if (rc) return rc;
+    return link_map(c, downstream, handlesAreIpc, c->linkDown, c->linkDownIpc);
+}
+
+int vpe_fill_sweep_linked(VpeContext* c) {
+    if (!c) return VPE_E_INVALID_ARG;
+    if (!c->prepared) return fail(c, VPE_E_NOT_READY, "vpe_fill_prepare has not been called");
+    if (!c->linkOwn) return fail(c, VPE_E_NOT_READY, "vpe_sheet_link_create has not been called");
+    cudaSetDevice(c->device);
+    return fill_region_impl(c, 0, c->g.NX, 0, c->g.NY, FILL_SWEEP_LINKED);
+}
+
+int vpe_sheet_link_status(VpeContext* c, int* timeouts) {
+    if (!c || !timeouts) return VPE_E_INVALID_ARG;
+    *timeouts = 0;
+    if (!c->linkOwn) return VPE_OK;
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    unsigned t = 0;
+    CUDA_TRY(c, cudaMemcpy(&t, static_cast<char*>(c->linkOwn) + link_layout(c->g).timeoutOff, sizeof(t), cudaMemcpyDeviceToHost));
+    *timeouts = (int)t;
+    return VPE_OK;
+}
 
 int vpe_march_device(VpeContext* c, const VpeCamera* cam, float* rgba_dev, int32_t* samples_dev) {
     if (!c || !cam || !rgba_dev) return fail(c, VPE_E_INVALID_ARG, "null argument");

@@ -170,6 +170,39 @@ class Engine:
     def fill_sweep_region(self, x0, x1, y0, y1):
         self._check(self.lib.vpe_fill_sweep_region(self._ctx, x0, x1, y0, y1))
 
+    # -- sheet link: the multi-GPU sweep over NVLink peer memory (CUDA library only) ---------
+    def sheet_link_create(self):
+        """Returns (64-byte CUDA IPC handle, device pointer) of this context's link buffer."""
+        h = (C.c_ubyte * 64)()
+        p = C.c_void_p()
+        self._check(self.lib.vpe_sheet_link_create(self._ctx, h, C.byref(p)))
+        return bytes(h), p.value
+
+    def sheet_link_connect(self, upstream, downstream):
+        """upstream / downstream: None, a 64-byte IPC handle (bytes; another process) or a device
+        pointer (int; a context of this process). Both must be of the same kind."""
+        kinds = {type(v) for v in (upstream, downstream) if v is not None}
+        if len(kinds) > 1:
+            raise ValueError("upstream and downstream must both be IPC handles or both device pointers")
+        ipc = bytes in kinds
+
+        def arg(v):
+            if v is None:
+                return None
+            if ipc:
+                return C.cast(C.create_string_buffer(v, 64), C.c_void_p)
+            return C.cast(C.pointer(C.c_void_p(int(v))), C.c_void_p)
+        keep = [arg(upstream), arg(downstream)]
+        self._check(self.lib.vpe_sheet_link_connect(self._ctx, keep[0], keep[1], 1 if ipc else 0))
+
+    def fill_sweep_linked(self):
+        self._check(self.lib.vpe_fill_sweep_linked(self._ctx))
+
+    def sheet_link_timeouts(self):
+        n = C.c_int(0)
+        self._check(self.lib.vpe_sheet_link_status(self._ctx, C.byref(n)))
+        return n.value
+
     def march(self, camera, want_samples=True, out=None, samples_out=None):
         c = _camera(camera)
         rgba = out if out is not None else np.empty((c.height, c.width, 4), dtype=np.float32)

@@ -25,6 +25,8 @@ partial rows to the band's owner, which composites them; rank 0 gathers the band
 The engine adapter is what touches memory: `CudaSlabEngine` (below) wraps the CUDA library and
 device tensors; the CPU tests drive the very same `SlabRenderer` with an adapter over the oracle.
 """
+import os
+
 import numpy as np
 
 
@@ -76,6 +78,11 @@ class SlabRenderer:
         if (self.z0, self.z1) != tuple(engine.slab):
             raise ValueError("engine owns slab %s, rank %d of %d must own %s" % (engine.slab, self.rank, self.world, (self.z0, self.z1)))
         self.bands = row_bands(gy, fill_bands if fill_bands is not None else default_fill_bands(engine.grid, engine.N, self.world))
+        # sheet link: engines that can hand the sheet over through peer memory (CUDA, one node) do so;
+        # fill_bands given explicitly (or VPE_SLAB_NCCL_SWEEP=1) keeps the NCCL send/recv band pipeline
+        self.linked = False
+        if self.world > 1 and fill_bands is None and hasattr(engine, "link_neighbours") and not os.environ.get("VPE_SLAB_NCCL_SWEEP"):
+            self.linked = bool(engine.link_neighbours(dist, self.rank, self.world))
 
     # -- fill -------------------------------------------------------------------------------------
     def fill(self, particles, emitter):
@@ -87,6 +94,11 @@ class SlabRenderer:
             e.fill_region(0, gx, 0, gy)             # fused: nothing to wait for
             return
         e.fill_density()                            # phase 1: the particle loop of the whole slab, no dependency
+        if self.linked:
+            # phase 2 in ONE kernel per rank: the sweep hands its exit values to the next rank's inbox over
+            # NVLink peer memory and raises a flag per block of voxel columns (k_sweep_columns<., true>)
+            e.fill_sweep_linked()
+            return
         sheet = e.sheet_tensor()                    # (NY*N, NX*N) fp32 view of the context's sheet
         for (y0, y1) in self.bands:                 # phase 2: the light sweep, pipelined through the ranks
             rows = sheet[y0 * n:y1 * n]
@@ -178,6 +190,25 @@ class CudaSlabEngine:
     def fill_sweep_region(self, x0, x1, y0, y1):
         self.eng.fill_sweep_region(x0, x1, y0, y1)
 
+    def link_neighbours(self, dist, rank, world):
+        """Exchange the CUDA IPC handles of the sheet link buffers and map the neighbours' buffers.
+        Returns False (the caller falls back to NCCL send/recv) when the ranks are not on one node."""
+        import socket
+        handle, _ = self.eng.sheet_link_create()
+        mine = (socket.gethostname(), handle)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        if len({h for h, _ in everyone}) != 1:
+            return False
+        up = everyone[rank - 1][1] if rank > 0 else None
+        down = everyone[rank + 1][1] if rank < world - 1 else None
+        self.eng.sheet_link_connect(up, down)
+        dist.barrier()
+        return True
+
+    def fill_sweep_linked(self):
+        self.eng.fill_sweep_linked()
+
     def sheet_tensor(self):
         if self._sheet is None:
             gx, gy, _ = self.grid
@@ -240,6 +271,7 @@ def bench_multi_gpu(args, metric, measured_peak_hbm, ClockSampler):
     dev = torch.device("cuda", local_rank)
     cfg_name = args.config or "cfg3"
     sc = scenes.make_scene(cfg_name)
+    torch.cuda.set_device(dev)
     eng = CudaSlabEngine(sc, rank, world, local_rank)
     r = SlabRenderer(eng, dist, fill_bands=args.fill_bands if getattr(args, "fill_bands", 0) else None)
     cam = sc["camera"]
@@ -327,8 +359,9 @@ def bench_multi_gpu(args, metric, measured_peak_hbm, ClockSampler):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %d^3 grid x %d^3 voxels, %d particles, %dx%d, %d steps/metavoxel" % (
             cfg_name, eng.grid[0], N, n, W, H, sc["rayMarchSteps"]),  # same string as bench.workload_name
-            "parallelism": "light-axis slabs x%d (fill: sheet rows over NCCL send/recv in %d bands; march: slab-local + "
-                           "all-to-all ordered compositing)" % (world, len(r.bands)),
+            "parallelism": "light-axis slabs x%d (fill: %s; march: slab-local + all-to-all ordered compositing)" % (
+                world, "sweep kernel hands the sheet to the next rank over NVLink peer memory, one launch" if r.linked
+                else "sheet rows over NCCL send/recv in %d bands" % len(r.bands)),
             "cache": "inputs larger than L2 (brick pools %.2f GB in total); no flush between iterations" % (pool / 1e9),
             "covered_metavoxels": int(covered), "particle_metavoxel_pairs": int(pairs)},
         "fill": {"value": voxels / (fill_ms * 1e-3), "unit": "voxels/s", "ms": fill_ms, "voxels": int(voxels)},
