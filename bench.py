@@ -337,6 +337,7 @@ def main():
     ap.add_argument("--config", default=None, help="cfg1..cfg5 (default: cfg3 at N=1)")
     ap.add_argument("--early-out", type=float, default=0.0, help="marchEarlyOutTransmittance (0 = exact reference semantics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rebalance", action="store_true", help="N>1: keep equal slabs (default: balance the slab boundaries during warm-up)")
     ap.add_argument("--fill-bands", type=int, default=0, help="N>1: row bands of the fill pipeline (default: one per metavoxel row)")
     args = ap.parse_args()
     if args.impl == "reference":

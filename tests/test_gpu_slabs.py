@@ -102,17 +102,33 @@ def test_linked_sweep_two_contexts_on_one_gpu():
         torch.cuda.synchronize()
         assert ranks[0].eng.sheet_link_timeouts() == 0 and ranks[1].eng.sheet_link_timeouts() == 0
         assert np.array_equal(ranks[1].eng.read_light_sheet(), one.read_light_sheet())
-    cov = 0
-    for z in range(gz):
-        owner = ranks[0] if z < ranks[0].slab[1] else ranks[1]
-        for y in range(gy):
-            for x in range(gx):
-                a, b = one.read_brick(x, y, z), owner.eng.read_brick(x, y, z)
-                assert (a is None) == (b is None)
-                if a is not None:
-                    cov += 1
-                    assert np.array_equal(a, b)
-    assert cov == one.stats()["numMetavoxelsCovered"]
+
+    def check_volume():
+        cov = 0
+        for z in range(gz):
+            owner = ranks[0] if z < ranks[0].slab[1] else ranks[1]
+            for y in range(gy):
+                for x in range(gx):
+                    a, b = one.read_brick(x, y, z), owner.eng.read_brick(x, y, z)
+                    assert (a is None) == (b is None)
+                    if a is not None:
+                        cov += 1
+                        assert np.array_equal(a, b)
+        assert cov == one.stats()["numMetavoxelsCovered"]
+    check_volume()
+    # load balancing moves the slab boundary between fills (SlabRenderer.rebalance): same volume again
+    ranks[0].set_slab(0, 3)
+    ranks[1].set_slab(3, gz)
+    with pytest.raises(vpe_b200.VpeError):
+        ranks[1].march_partial(sc["camera"])  # the old slab's volume is gone: fill first
+    for e in ranks:
+        e.fill_prepare(sc["particles"], sc["emitter"])
+        e.fill_density()
+    for e in ranks:
+        e.fill_sweep_linked()
+    torch.cuda.synchronize()
+    assert np.array_equal(ranks[1].eng.read_light_sheet(), one.read_light_sheet())
+    check_volume()
 
 
 def test_linked_sweep_reports_a_missing_peer(monkeypatch):

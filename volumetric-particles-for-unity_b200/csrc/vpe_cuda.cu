@@ -597,9 +597,13 @@ int vpe_set_config(VpeContext* c, const VpeConfig* cfg) {
     std::string why;
     if (validate_config(c2, why)) return fail(c, VPE_E_INVALID_ARG, why.c_str());
     if (c2.numMetavoxelsX != c->cfg.numMetavoxelsX || c2.numMetavoxelsY != c->cfg.numMetavoxelsY ||
-        c2.numMetavoxelsZ != c->cfg.numMetavoxelsZ || c2.numVoxelsInMetavoxel != c->cfg.numVoxelsInMetavoxel ||
-        c2.slabZBegin != c->cfg.slabZBegin || c2.slabZEnd != c->cfg.slabZEnd)
-        return fail(c, VPE_E_INVALID_ARG, "grid dims, voxel count and slab are fixed at create");
+        c2.numMetavoxelsZ != c->cfg.numMetavoxelsZ || c2.numVoxelsInMetavoxel != c->cfg.numVoxelsInMetavoxel)
+        return fail(c, VPE_E_INVALID_ARG, "grid dims and voxel count are fixed at create");
+    if (c2.slabZBegin != c->cfg.slabZBegin || c2.slabZEnd != c->cfg.slabZEnd) {
+        // the slab may move between fills (load balancing, slabs.py): the volume of the old slab is gone
+        c->prepared = false;
+        c->filledOnce = false;
+    }
     c->cfg = c2;
     rebuild_grid_params(c);  // SetGridScale re-places the metavoxels (VPR.cs:1059-1063)
     return VPE_OK;

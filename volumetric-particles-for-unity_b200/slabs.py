@@ -52,6 +52,48 @@ def image_band(height, world, rank):
     return min(rank * per, height), min((rank + 1) * per, height)
 
 
+def balance_slabs(density_cost, sweep_cost, march_cost, world, prepare=0.1, lag=0.07):
+    """Contiguous light-axis slabs [z0, z1) per rank that minimise the modelled frame time.
+
+    Per-slice costs (ms): density_cost = the particle loop, sweep_cost = the light sweep, march_cost = the
+    ray march. Model of one frame on rank r owning slices [a, b) (what tools/slab_trace.py shows):
+        density ends   d_r = prepare + sum(density_cost[a:b])
+        sweep ends     s_r = max(d_r + sum(sweep_cost[a:b]), s_{r-1} + lag)     (the sheet chain)
+        march ends     e_r = s_r + sum(march_cost[a:b])
+    and the frame ends at max_r e_r (the compositing exchange waits for every rank). The sweep of a rank
+    cannot end before that of the rank nearer the light, so ranks late in the chain should carry less
+    march work; exact search by dynamic programming over (rank, first slice) with Pareto-pruned states."""
+    nz = len(density_cost)
+    if not (1 <= world <= nz):
+        raise ValueError("need 1 <= world <= number of slices")
+    cd = np.concatenate([[0.0], np.cumsum(np.asarray(density_cost, dtype=np.float64))])
+    cs = np.concatenate([[0.0], np.cumsum(np.asarray(sweep_cost, dtype=np.float64))])
+    cm = np.concatenate([[0.0], np.cumsum(np.asarray(march_cost, dtype=np.float64))])
+    # states[start] = list of (sweep_end_prev, worst_end_so_far, cuts) not dominated by another
+    states = {0: [(-1e30, 0.0, ())]}
+    for r in range(world):
+        nxt = {}
+        remaining = world - r - 1
+        for a, lst in states.items():
+            hi = nz - remaining
+            ends = [nz] if remaining == 0 else range(a + 1, hi + 1)
+            for b in ends:
+                d = prepare + cd[b] - cd[a]
+                sw, ma = cs[b] - cs[a], cm[b] - cm[a]
+                for (sp, worst, cuts) in lst:
+                    se = max(d + sw, sp + lag)
+                    cand = (se, max(worst, se + ma), cuts + (b,))
+                    cur = nxt.setdefault(b, [])
+                    if any(o[0] <= cand[0] and o[1] <= cand[1] for o in cur):
+                        continue
+                    cur[:] = [o for o in cur if not (cand[0] <= o[0] and cand[1] <= o[1])]
+                    cur.append(cand)
+        states = nxt
+    best = min(states[nz], key=lambda t: t[1])
+    cuts = (0,) + best[2]
+    return [(cuts[i], cuts[i + 1]) for i in range(world)], best[1]
+
+
 def default_fill_bands(grid, n_voxels, world, min_ctas_per_launch=512):
     """Bands of metavoxel rows for the fill pipeline: as many as possible (the pipeline bubble is
     (R-1)/(T+R-1)) while one band's launch still has >= min_ctas_per_launch CTAs (k_fill_columns uses
@@ -80,6 +122,8 @@ class SlabRenderer:
         self.bands = row_bands(gy, fill_bands if fill_bands is not None else default_fill_bands(engine.grid, engine.N, self.world))
         # sheet link: engines that can hand the sheet over through peer memory (CUDA, one node) do so;
         # fill_bands given explicitly (or VPE_SLAB_NCCL_SWEEP=1) keeps the NCCL send/recv band pipeline
+        self.profile = False          # record device times of the density pass and the march kernel (rebalance)
+        self._times = None
         self.linked = False
         if self.world > 1 and fill_bands is None and hasattr(engine, "link_neighbours") and not os.environ.get("VPE_SLAB_NCCL_SWEEP"):
             self.linked = bool(engine.link_neighbours(dist, self.rank, self.world))
@@ -93,7 +137,11 @@ class SlabRenderer:
         if self.world == 1:
             e.fill_region(0, gx, 0, gy)             # fused: nothing to wait for
             return
+        t0 = e.record_event() if self.profile else None
         e.fill_density()                            # phase 1: the particle loop of the whole slab, no dependency
+        t1 = e.record_event() if self.profile else None
+        if self.profile:
+            self._times = [t0, t1]
         if self.linked:
             # phase 2 in ONE kernel per rank: the sweep hands its exit values to the next rank's inbox over
             # NVLink peer memory and raises a flag per block of voxel columns (k_sweep_columns<., true>)
@@ -109,6 +157,38 @@ class SlabRenderer:
             if self.rank < self.world - 1:
                 e.sheet_read(y0, y1)
                 d.send(rows, dst=self.rank + 1)
+
+    # -- load balance -----------------------------------------------------------------------------
+    def set_slab(self, z0, z1):
+        self.e.set_slab(z0, z1)
+        self.z0, self.z1 = z0, z1
+
+    def rebalance(self):
+        """Move the slab boundaries so that the modelled frame time (balance_slabs) is minimal, from the
+        device times of the last profiled frame (self.profile = True during fill() and march()): each rank's
+        density and march-kernel time is spread evenly over its slices, which gives a per-slice cost profile
+        of the whole grid; all ranks compute the same partition from the same gathered numbers. The volume
+        must be filled again afterwards. Returns the new list of slabs."""
+        e, d = self.e, self.dist
+        if self.world == 1 or self._times is None:
+            return [(self.z0, self.z1)]
+        density_ms = e.elapsed_ms(self._times[0], self._times[1])
+        march_ms = float(e.stats()["marchKernelMs"])
+        mine = (self.z0, self.z1, density_ms, march_ms)
+        rows = [None] * self.world
+        d.all_gather_object(rows, mine)
+        nz = e.grid[2]
+        dc, mc = np.zeros(nz), np.zeros(nz)
+        for (a, b, dm, mm) in rows:
+            dc[a:b] = dm / (b - a)
+            mc[a:b] = mm / (b - a)
+        # the sweep moves 16 bytes per voxel of a covered metavoxel; ~0.6 of the HBM rate measured alone
+        gx, gy, _ = e.grid
+        sweep = np.full(nz, gx * gy * float(e.N) ** 3 * 16.0 / 4.0e12 * 1e3)
+        slabs_, _ = balance_slabs(dc, sweep, mc, self.world)
+        self.set_slab(*slabs_[self.rank])
+        self._times = None
+        return slabs_
 
     # -- march ------------------------------------------------------------------------------------
     def march(self, camera, gather=True, count_samples=True):
@@ -209,6 +289,19 @@ class CudaSlabEngine:
     def fill_sweep_linked(self):
         self.eng.fill_sweep_linked()
 
+    def set_slab(self, z0, z1):
+        self.eng.set_config(slabZBegin=int(z0), slabZEnd=int(z1))
+        self.slab = (int(z0), int(z1))
+
+    def record_event(self):
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record(self.torch.cuda.current_stream(self.device))
+        return ev
+
+    def elapsed_ms(self, a, b):
+        b.synchronize()
+        return float(a.elapsed_time(b))
+
     def sheet_tensor(self):
         if self._sheet is None:
             gx, gy, _ = self.grid
@@ -296,6 +389,16 @@ def bench_multi_gpu(args, metric, measured_peak_hbm, ClockSampler):
         return float(t.item())
 
     warm = max(3, args.warmup)
+    slab_list = [slab_range(eng.grid[2], world, q) for q in range(world)]
+    if world > 1 and not getattr(args, "no_rebalance", False):
+        # untimed: measure a frame, move the slab boundaries (SlabRenderer.rebalance), twice
+        for _ in range(2):
+            r.profile = True
+            for _ in range(2):
+                r.fill(parts_dev, sc["emitter"])
+                r.march(cam, gather=False, count_samples=False)
+            slab_list = r.rebalance()
+            r.profile = False
     for _ in range(warm):
         r.fill(parts_dev, sc["emitter"])
         r.march(cam, gather=False)
@@ -362,6 +465,7 @@ def bench_multi_gpu(args, metric, measured_peak_hbm, ClockSampler):
             "parallelism": "light-axis slabs x%d (fill: %s; march: slab-local + all-to-all ordered compositing)" % (
                 world, "sweep kernel hands the sheet to the next rank over NVLink peer memory, one launch" if r.linked
                 else "sheet rows over NCCL send/recv in %d bands" % len(r.bands)),
+            "slabs": [list(x) for x in slab_list],
             "cache": "inputs larger than L2 (brick pools %.2f GB in total); no flush between iterations" % (pool / 1e9),
             "covered_metavoxels": int(covered), "particle_metavoxel_pairs": int(pairs)},
         "fill": {"value": voxels / (fill_ms * 1e-3), "unit": "voxels/s", "ms": fill_ms, "voxels": int(voxels)},
