@@ -132,6 +132,14 @@ int vpe_set_displacement_cubemap(VpeContext* ctx, const uint8_t* r8, int edge);
  * NULL = no occluders (all 1.0). */
 int vpe_set_light_depth_map(VpeContext* ctx, const float* depth01);
 
+/* ≙ lightCamera.RenderWithShader(generateLightDepthMapShader), VPR.cs:184, with the light camera of
+ * InitCameraAtLight (VPR.cs:320-367) and GenerateLightDepthMap.shader:6 (Cull Front, ZWrite On, ZTest
+ * Less): rasterises the scene's occluders, numTriangles x 3 world-space vertices (9 floats each, Unity
+ * winding: clockwise = front), into the context's light depth map; later fills read it (Fill.shader:216).
+ * vpe_read_light_depth_map is the test hook ((NY*N) rows x (NX*N) floats). */
+int vpe_render_light_depth_map(VpeContext* ctx, const float* trianglesWorld, int numTriangles);
+int vpe_read_light_depth_map(VpeContext* ctx, float* depth01);
+
 /* ≙ BinParticlesToMetavoxels + FillMetavoxels, VPR.cs:397-520 (+ FillVolume.shader).
  * emitter = particleSys.transform. */
 int vpe_fill(VpeContext* ctx, const VpeParticle* particles, int n, const VpeTransform* emitter);
@@ -141,6 +149,26 @@ int vpe_fill(VpeContext* ctx, const VpeParticle* particles, int n, const VpeTran
  * as float4, no 8-bit quantisation); row 0 is screen-space y = 0 of March.shader:189.
  * samples: optional height*width int32 = loop iterations per pixel (≙ _ShowNumSamples). */
 int vpe_march(VpeContext* ctx, const VpeCamera* cam, float* rgba, int32_t* samples);
+
+/* What surrounds the march in the reference's frame; defaults = all zero.
+ * Non-default options are rendered by the general march kernel, not the specialised fast one. */
+typedef struct VpeMarchOptions {
+    int32_t targetFormat;    /* 0 = float4; 1 = UNORM8 like the reference's ARGB32 particlesRT (VPR.cs:228):
+                                the target is quantised after every metavoxel's ROP blend                 */
+    int32_t debugMode;       /* 0 = off; 1 = draw order (March.shader:123-138,170); 2 = blend function
+                                (:174-181); 3 = sample-count bands (:283-299)                              */
+    const float* sceneDepth; /* host, sceneHeight*sceneWidth eye-space depths of the opaque scene, or NULL:
+                                ≙ `ZTest Less` against mainSceneRT.depthBuffer (March.shader:14, VPR.cs:204):
+                                a metavoxel's fragment exists only where its back face is nearer            */
+    int32_t sceneWidth, sceneHeight;
+} VpeMarchOptions;
+int vpe_set_march_options(VpeContext* ctx, const VpeMarchOptions* options);
+
+/* ≙ Graphics.Blit(particlesRT, mainSceneRT, matBlendParticles), VPR.cs:210, with
+ * CompositeParticles.shader:10 `Blend One OneMinusSrcAlpha, One One`: scene.rgb = p.rgb + (1-p.a)*scene.rgb,
+ * scene.a += p.a; host buffers, numPixels*4 floats each; targetFormat 1 quantises the result to UNORM8. */
+int vpe_composite_scene(VpeContext* ctx, const float* particlesRgba, float* sceneRgba, int numPixels,
+                        int targetFormat);
 
 /* Same, for a list of pixel indices (y*width + x); rgba is n*4, samples n. Used for parity at
  * sizes where the scalar oracle cannot render the full image. */

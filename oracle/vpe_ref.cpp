@@ -262,6 +262,10 @@ struct VpeContext {
     std::vector<float> partOpacity;
     bool prepared = false;
     VpeStats stats;
+    // march options (vpe_set_march_options): 8-bit target, debug views, scene depth test
+    int targetFormat = 0, debugMode = 0;
+    std::vector<float> sceneDepth;  // eye-space depth per pixel (empty = no scene geometry)
+    int sceneW = 0, sceneH = 0;
 
     int NX() const { return cfg.numMetavoxelsX; }
     int NY() const { return cfg.numMetavoxelsY; }
@@ -709,13 +713,38 @@ RaySetup ray_setup(const VpeContext* c, const MarchPass* mp, int px, int py) {
 
 // March.shader:166-302 frag for one (pixel, metavoxel); returns false when the shader returns
 // "seethrough" before the loop (no intersection).  src = (rgb, 1 - transmittance).
+// sceneEyeDepth: eye-space depth of the opaque scene at this pixel (3e38 = nothing there). orderIndex /
+// numCovered: _OrderIndex / _NumMetavoxelsCovered of the draw-order debug view.
 bool march_frag(const VpeContext* c, const RaySetup& rs, const MarchPass::Draw& dr, float src[4], int* samples,
-                std::vector<uint8_t>* footprint = nullptr) {
+                std::vector<uint8_t>* footprint = nullptr, float sceneEyeDepth = 3.0e38f, int orderIndex = 0, int numCovered = 0) {
     const int N = c->N();
     V3 o = mul4(dr.C2M, rs.start, 1.0f);                     // :217
     V3 d = normalize_hlsl(mul4(dr.C2M, rs.dir, 0.0f));       // :218
     float t1, t2;
     if (!intersect_box(o, d, &t1, &t2)) { src[0] = src[1] = src[2] = src[3] = 0.0f; return false; }  // :229-231
+    {
+        // ≙ `Cull Front ... ZTest Less` against mainSceneRT.depthBuffer (March.shader:14, VPR.cs:204): the fragment
+        // exists only where the cube's back face (the ray's exit point, t2) is nearer than the opaque scene.
+        // A metavoxel-space length t is a camera-space length t * mvScale along the ray.
+        // Faces behind the camera are clipped, not rasterised (such a fragment could only hold samples behind
+        // tCamera, i.e. none: this matters for the debug views alone).
+        float exitEyeDepth = -(rs.start.z + (t2 * c->cfg.mvScale) * rs.dir.z);
+        if (!(exitEyeDepth > 0.0f && exitEyeDepth < sceneEyeDepth)) { src[0] = src[1] = src[2] = src[3] = 0.0f; return false; }
+    }
+    if (c->debugMode == 1) {  // DrawOrderColoring, March.shader:123-138,170-173
+        int numColorsPerChannel = (int)ceilf((float)numCovered / 3.0f);
+        int channelSelect = orderIndex / numColorsPerChannel;
+        int channelIndex = orderIndex % numColorsPerChannel;
+        float channelIntensity = (float)(numColorsPerChannel - channelIndex) / (float)numColorsPerChannel;
+        src[0] = src[1] = src[2] = 0.0f; src[3] = 1.0f;
+        src[channelSelect == 0 ? 1 : (channelSelect == 1 ? 2 : 0)] = channelIntensity;
+        return true;
+    }
+    if (c->debugMode == 2) {  // March.shader:174-181
+        if (dr.over) { src[0] = 0.5f; src[1] = 0.5f; src[2] = 0.0f; src[3] = 1.0f; }
+        else { src[0] = 0.0f; src[1] = 0.5f; src[2] = 0.5f; src[3] = 1.0f; }
+        return true;
+    }
     const float step = rs.stepSize;
     int tEntry = ftoi(ceilf(t1 / step));                     // :236
     int tExit = ftoi(floorf(t2 / step));                     // :237
@@ -756,8 +785,23 @@ bool march_frag(const VpeContext* c, const RaySetup& rs, const MarchPass::Draw& 
         n++;
     }
     *samples += n;
+    if (c->debugMode == 3) {  // sample-count bands, March.shader:283-299
+        static const float bands[7][4] = {{0.0f, 0.2f, 0.0f, 0.5f}, {0.0f, 0.5f, 0.0f, 0.5f}, {0.5f, 0.5f, 0.0f, 0.5f}, {0.6f, 0.4f, 0.0f, 0.5f},
+                                          {0.6f, 0.0f, 0.0f, 0.5f}, {0.8f, 0.0f, 0.0f, 0.5f}, {1.0f, 0.0f, 0.0f, 0.5f}};
+        int b = n < 5 ? 0 : n < 10 ? 1 : n < 20 ? 2 : n < 30 ? 3 : n < 40 ? 4 : n < 50 ? 5 : 6;
+        for (int ch = 0; ch < 4; ch++) src[ch] = bands[b][ch];
+        return true;
+    }
     src[0] = result[0]; src[1] = result[1]; src[2] = result[2]; src[3] = 1.0f - transmittance;  // :301
     return true;
+}
+
+// float -> UNORM8 -> float, as the ROP of an ARGB32 target stores and re-reads it (particlesRT, VPR.cs:228):
+// saturate, scale by 255, round half up.
+inline float quantize_unorm8(float x) {
+    float v = fminf(fmaxf(x, 0.0f), 1.0f);
+    v = floorf(v * 255.0f + 0.5f);
+    return v / 255.0f;
 }
 
 // Fixed-function blend between metavoxels (March.shader:14-18, VPR.cs:659-662 / 688-691).
@@ -776,6 +820,10 @@ int march_pixels_impl(VpeContext* c, const VpeCamera* cam, const int32_t* pixels
     if (!c->lightSet) return fail(c, VPE_E_NOT_READY, "vpe_set_light has not been called");
     if (!c->prepared) return fail(c, VPE_E_NOT_READY, "vpe_fill has not been called");
     if (cam->width < 1 || cam->height < 1) return fail(c, VPE_E_INVALID_ARG, "bad image size");
+    if (!c->sceneDepth.empty() && (c->sceneW != cam->width || c->sceneH != cam->height))
+        return fail(c, VPE_E_INVALID_ARG, "scene depth buffer does not match the camera's image size");
+    if ((overPart || underPart) && (c->targetFormat != 0 || c->debugMode != 0 || !c->sceneDepth.empty()))
+        return fail(c, VPE_E_UNSUPPORTED, "march options are not available for slab partial images");
     double t0 = now_ms();
     MarchPass mp;
     build_march_pass(c, cam, &mp);
@@ -793,8 +841,11 @@ int march_pixels_impl(VpeContext* c, const VpeCamera* cam, const int32_t* pixels
         float dOver[4] = {0, 0, 0, 0}, dUnder[4] = {0, 0, 0, 0};
         int ns = 0;
         const float pcx = (float)px + 0.5f, pcy = (float)py + 0.5f;
+        const float sceneEye = c->sceneDepth.empty() ? 3.0e38f : c->sceneDepth[(size_t)py * cam->width + px];
+        int orderIndex = -1;
         for (const MarchPass::Draw& dr : mp.draws) {
             float src[4];
+            orderIndex++;  // RenderMetavoxel(xx, yy, zz, mvCount++), VPR.cs:675,705
             if (pcx < dr.px0 || pcx > dr.px1 || pcy < dr.py0 || pcy > dr.py1) continue;  // not rasterised
             if (!c->filled[c->mvIndex(dr.x, dr.y, dr.z)]) {
                 // region-filled oracle (vpe_fill_region on a subset): a ray may only enter filled metavoxels
@@ -809,8 +860,10 @@ int march_pixels_impl(VpeContext* c, const VpeCamera* cam, const int32_t* pixels
                 fp = &(*footprints)[c->mvIndex(dr.x, dr.y, dr.z)];
                 if (fp->empty()) fp->assign((size_t)c->N() * c->N() * c->N(), 0);
             }
-            if (!march_frag(c, rs, dr, src, &ns, fp)) continue;  // seethrough: blending (0,0,0,0) is the identity
+            if (!march_frag(c, rs, dr, src, &ns, fp, sceneEye, orderIndex, (int)mp.draws.size())) continue;  // seethrough: blending (0,0,0,0) is the identity
             rop_blend(dst, src, dr.over);
+            if (c->targetFormat == 1)
+                for (int ch = 0; ch < 4; ch++) dst[ch] = quantize_unorm8(dst[ch]);
             if (overPart && dr.over) rop_blend(dOver, src, true);
             if (underPart && !dr.over) rop_blend(dUnder, src, false);
         }
@@ -923,6 +976,93 @@ int vpe_set_light_depth_map(VpeContext* c, const float* depth01) {
     if (!depth01) { c->depthMap.clear(); return VPE_OK; }
     size_t n = (size_t)c->NX() * c->N() * c->NY() * c->N();
     c->depthMap.assign(depth01, depth01 + n);
+    return VPE_OK;
+}
+
+// ≙ lightCamera.RenderWithShader(generateLightDepthMapShader) (VPR.cs:184) with the camera of InitCameraAtLight
+// (VPR.cs:320-367: orthographic, extents +-NX*s/2 x +-NY*s/2, near/far 0.3/1000, at centre - forward*200, the
+// light's rotation) and GenerateLightDepthMap.shader:6 (Cull Front, ZWrite On, ZTest Less; depth only).
+// Rasteriser restated: pixel centres, top-left rule, fp32 edge functions, affine depth (orthographic).
+// Unity front faces are clockwise; with Cull Front the counter-clockwise (back) faces are drawn.
+int vpe_render_light_depth_map(VpeContext* c, const float* tris, int numTriangles) {
+    if (!c || (!tris && numTriangles > 0) || numTriangles < 0) return fail(c, VPE_E_INVALID_ARG, "bad triangle list");
+    if (!c->lightSet) return fail(c, VPE_E_NOT_READY, "vpe_set_light has not been called");
+    const int W = c->NX() * c->N(), H = c->NY() * c->N();
+    c->depthMap.assign((size_t)W * H, 1.0f);  // CameraClearFlags.Depth, VPR.cs:347
+    const float r = (float)c->NX() * c->cfg.mvScale * 0.5f, t = (float)c->NY() * c->cfg.mvScale * 0.5f;  // VPR.cs:340
+    const float zn = c->cfg.lightNear, zf = c->cfg.lightFar;
+    for (int i = 0; i < numTriangles; i++) {
+        float sx[3], sy[3], sz[3];
+        for (int k = 0; k < 3; k++) {
+            V3 p = mul4(c->W2LC, v3(tris[i * 9 + k * 3], tris[i * 9 + k * 3 + 1], tris[i * 9 + k * 3 + 2]), 1.0f);
+            sx[k] = (p.x / r * 0.5f + 0.5f) * (float)W;   // pixel coordinates; row 0 = light-space y = -t (uv.y = 0)
+            sy[k] = (p.y / t * 0.5f + 0.5f) * (float)H;
+            sz[k] = (p.z - zn) / (zf - zn);               // D3D orthographic depth, linear in [0,1]
+        }
+        const float area = (sx[1] - sx[0]) * (sy[2] - sy[0]) - (sy[1] - sy[0]) * (sx[2] - sx[0]);
+        if (!(area > 0.0f)) continue;  // clockwise = front face: culled (Cull Front); degenerate: nothing to draw
+        const float minx = fminf(sx[0], fminf(sx[1], sx[2])), maxx = fmaxf(sx[0], fmaxf(sx[1], sx[2]));
+        const float miny = fminf(sy[0], fminf(sy[1], sy[2])), maxy = fmaxf(sy[0], fmaxf(sy[1], sy[2]));
+        const int x0 = std::max(0, (int)floorf(minx - 0.5f)), x1 = std::min(W - 1, (int)ceilf(maxx - 0.5f));
+        const int y0 = std::max(0, (int)floorf(miny - 0.5f)), y1 = std::min(H - 1, (int)ceilf(maxy - 0.5f));
+        for (int y = y0; y <= y1; y++)
+            for (int x = x0; x <= x1; x++) {
+                const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+                float w[3];
+                bool inside = true;
+                for (int k = 0; k < 3 && inside; k++) {
+                    const int a = (k + 1) % 3, b = (k + 2) % 3;  // edge opposite vertex k
+                    const float ex = sx[b] - sx[a], ey = sy[b] - sy[a];
+                    w[k] = ex * (py - sy[a]) - ey * (px - sx[a]);
+                    // top-left rule for a counter-clockwise triangle in a y-up raster: an edge owns its points
+                    // if it is a left edge (going down) or a horizontal top edge (going left)
+                    const bool owns = ey < 0.0f || (ey == 0.0f && ex < 0.0f);
+                    if (w[k] < 0.0f || (w[k] == 0.0f && !owns)) inside = false;
+                }
+                if (!inside) continue;
+                const float z = ((w[0] / area) * sz[0] + (w[1] / area) * sz[1]) + (w[2] / area) * sz[2];
+                if (!(z >= 0.0f && z <= 1.0f)) continue;  // near / far clip
+                float& dst = c->depthMap[(size_t)y * W + x];
+                if (z < dst) dst = z;  // ZTest Less, ZWrite On
+            }
+    }
+    return VPE_OK;
+}
+
+int vpe_read_light_depth_map(VpeContext* c, float* depth01) {
+    if (!c || !depth01) return VPE_E_INVALID_ARG;
+    const size_t n = (size_t)c->NX() * c->N() * c->NY() * c->N();
+    for (size_t i = 0; i < n; i++) depth01[i] = c->depthMap.empty() ? 1.0f : c->depthMap[i];
+    return VPE_OK;
+}
+
+int vpe_set_march_options(VpeContext* c, const VpeMarchOptions* o) {
+    if (!c || !o) return VPE_E_INVALID_ARG;
+    if (o->targetFormat < 0 || o->targetFormat > 1 || o->debugMode < 0 || o->debugMode > 3) return fail(c, VPE_E_INVALID_ARG, "bad march option");
+    if (o->sceneDepth && (o->sceneWidth < 1 || o->sceneHeight < 1)) return fail(c, VPE_E_INVALID_ARG, "bad scene depth size");
+    c->targetFormat = o->targetFormat;
+    c->debugMode = o->debugMode;
+    c->sceneDepth.clear();
+    if (o->sceneDepth) {
+        c->sceneW = o->sceneWidth; c->sceneH = o->sceneHeight;
+        c->sceneDepth.assign(o->sceneDepth, o->sceneDepth + (size_t)o->sceneWidth * o->sceneHeight);
+    }
+    return VPE_OK;
+}
+
+// ≙ Graphics.Blit(particlesRT, mainSceneRT, matBlendParticles) (VPR.cs:210) with CompositeParticles.shader:10
+// `Blend One OneMinusSrcAlpha, One One`.
+int vpe_composite_scene(VpeContext* c, const float* particles, float* scene, int numPixels, int targetFormat) {
+    if (!c || !particles || !scene || numPixels < 0 || targetFormat < 0 || targetFormat > 1) return fail(c, VPE_E_INVALID_ARG, "bad argument");
+    for (size_t i = 0; i < (size_t)numPixels; i++) {
+        const float* s = particles + i * 4;
+        float* d = scene + i * 4;
+        const float k = 1.0f - s[3];
+        d[0] = s[0] + d[0] * k; d[1] = s[1] + d[1] * k; d[2] = s[2] + d[2] * k;
+        d[3] = s[3] + d[3];
+        if (targetFormat == 1)
+            for (int ch = 0; ch < 4; ch++) d[ch] = quantize_unorm8(d[ch]);
+    }
     return VPE_OK;
 }
 

@@ -50,7 +50,8 @@ def test_struct_layout_matches_the_c_header(tmp_path):
               "VpeConfig": [f for f, _ in _abi.VpeConfig._fields_],
               "VpeParticle": [f for f, _ in _abi.VpeParticle._fields_],
               "VpeCamera": [f for f, _ in _abi.VpeCamera._fields_],
-              "VpeStats": [f for f, _ in _abi.VpeStats._fields_]}
+              "VpeStats": [f for f, _ in _abi.VpeStats._fields_],
+              "VpeMarchOptions": [f for f, _ in _abi.VpeMarchOptions._fields_]}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vpe.h"', "int main(void){"]
     for s, fs in fields.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (s, s))

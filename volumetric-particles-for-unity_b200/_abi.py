@@ -62,6 +62,11 @@ class VpeStats(C.Structure):
     ]
 
 
+class VpeMarchOptions(C.Structure):
+    _fields_ = [("targetFormat", C.c_int32), ("debugMode", C.c_int32), ("sceneDepth", C.c_void_p),
+                ("sceneWidth", C.c_int32), ("sceneHeight", C.c_int32)]
+
+
 assert C.sizeof(VpeParticle) == 28
 
 _P = C.c_void_p
@@ -75,6 +80,10 @@ PROTOTYPES = {
     "vpe_set_light": (C.c_int, [_P, C.POINTER(VpeTransform), C.POINTER(C.c_float)]),
     "vpe_set_displacement_cubemap": (C.c_int, [_P, _P, C.c_int]),
     "vpe_set_light_depth_map": (C.c_int, [_P, _P]),
+    "vpe_render_light_depth_map": (C.c_int, [_P, _P, C.c_int]),
+    "vpe_read_light_depth_map": (C.c_int, [_P, _P]),
+    "vpe_set_march_options": (C.c_int, [_P, C.POINTER(VpeMarchOptions)]),
+    "vpe_composite_scene": (C.c_int, [_P, _P, _P, C.c_int, C.c_int]),
     "vpe_fill": (C.c_int, [_P, _P, C.c_int, C.POINTER(VpeTransform)]),
     "vpe_march": (C.c_int, [_P, C.POINTER(VpeCamera), _P, _P]),
     "vpe_march_pixels": (C.c_int, [_P, C.POINTER(VpeCamera), _P, C.c_int, _P, _P]),

@@ -86,6 +86,8 @@ struct MarchParams {
     int tileLog2W;               // warp pixel tile = 2^tileLog2W x (32 >> tileLog2W)
     int rowStride;               // = GridParams::rowStride
     int gray;                    // layout of the bricks being marched (GridParams::gray at fill time)
+    int targetFormat, debugMode; // VpeMarchOptions (legacy kernel only)
+    int numCovered;              // _NumMetavoxelsCovered (VPR.cs:755)
 };
 
 }  // namespace vpe

@@ -88,6 +88,15 @@ struct VpeContext {
     bool linkUpIpc = false, linkDownIpc = false;
     int linkBlocks = 0;
     unsigned linkEpoch = 0;
+    // around the path: light camera, march options
+    Affine w2lc;                     // lightCamera.transform.worldToLocalMatrix (VPR.cs:365-366)
+    int targetFormat = 0, debugMode = 0;
+    DevBuf<float> dSceneDepth;
+    int sceneW = 0, sceneH = 0;
+    bool sceneDepthSet = false;
+    DevBuf<int> dOrderOf;
+    DevBuf<float> dTris;
+    DevBuf<float4> dScene;
     bool depthSet = false;
     bool bricksGray = false;         // layout of the bricks of the last fill (GridParams::gray at that time)
     int cubeEdge = 0;
@@ -162,6 +171,7 @@ void rebuild_grid_params(VpeContext* c) {
         F3 lc = f3(g.center.x - c->lightFwdRaw.x * k.lightCameraDistance, g.center.y - c->lightFwdRaw.y * k.lightCameraDistance,
                    g.center.z - c->lightFwdRaw.z * k.lightCameraDistance);
         Affine w2lc = affine_inverse(trs(lc, c->lightRot, 1.0f));
+        c->w2lc = w2lc;
         for (int j = 0; j < 4; j++) g.w2lcRow2[j] = w2lc.m[2][j];
     }
     g.oneVoxelSize = g.sb / g.Nf;  // Fill.shader:160
@@ -412,6 +422,14 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     m.wrap = k.numBorderVoxels == 0 ? 1 : 0;
     m.rowStride = g.rowStride;
     m.gray = c->bricksGray ? 1 : 0;
+    // march options (vpe_set_march_options): rendered by the general kernel
+    const bool optionsActive = c->targetFormat != 0 || c->debugMode != 0 || c->sceneDepthSet;
+    if (optionsActive && (partial || footprint)) return fail(c, VPE_E_UNSUPPORTED, "march options are not available for slab partial images");
+    if (c->sceneDepthSet && (c->sceneW != cam->width || c->sceneH != cam->height || pixelsDev))
+        return fail(c, VPE_E_INVALID_ARG, "scene depth buffer does not match the camera's image (full-image march only)");
+    m.targetFormat = c->targetFormat;
+    m.debugMode = c->debugMode;
+    m.numCovered = c->nCovered;
 
     CUDA_TRY(c, cudaEventRecord(c->evMarch0, c->stream));
     c->marchTimed = false;
@@ -422,6 +440,13 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     a.mvCam = c->dMvCam.p; a.rankAsc = c->dRank.p; a.bricks = c->dBricks.p; a.pixels = pixelsDev;
     a.rgba = rgbaDev; a.under = underDev; a.samples = samplesDev; a.totalSamples = c->dTotalSamples.p;
     a.footprint = footprint;
+    a.sceneDepth = c->sceneDepthSet ? c->dSceneDepth.p : nullptr;
+    a.orderOf = nullptr;
+    if (c->debugMode == 1) {
+        CUDA_TRY(c, c->dOrderOf.ensure(c->numCells));
+        k_order_index<<<div_up(c->numCells, 128), 128, 0, c->stream>>>(g, m, c->dBrickOf.p, c->dRank.p, c->dSliceStart.p, c->dOrderOf.p);
+        a.orderOf = c->dOrderOf.p;
+    }
     const bool skip = c->occCells > 0 && !getenv("VPE_MARCH_NO_SKIP");
     a.occ = skip ? c->dOcc.p : nullptr; a.occCells = c->occCells;
     // Warp pixel tile. Measured on cfg3 (profiles/): the compact 8x4 tile wins over strips that follow
@@ -441,7 +466,7 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     }
     CUDA_TRY(c, cudaEventRecord(c->evMarchK0, c->stream));
     if (m.numPixels > 0) {
-        const bool legacy = m.wrap || getenv("VPE_MARCH_LEGACY");
+        const bool legacy = m.wrap || optionsActive || getenv("VPE_MARCH_LEGACY");
         const bool gray = c->bricksGray;  // the layout the fill wrote (z-paired grey texels or half4)
         // k_march_merged trades divergence (26.6 instead of 22.6 active lanes) for L1 bank conflicts (lanes in
         // different bricks): 9.2 vs 8.9 ms on cfg3 with 8-byte texels (profiles/). Opt-in until the texel fetch is cheaper.
@@ -573,6 +598,7 @@ int vpe_destroy(VpeContext* c) {
     c->dCube.release(); c->dCubeFp.release(); c->dDepth.release(); c->dSheet.release(); c->dBricks.release(); c->dOcc.release(); c->dMvCam.release();
     c->dRank.release(); c->dPixels.release(); c->dSamples.release(); c->dImage.release(); c->dImage2.release();
     c->dTotalSamples.release(); c->dParts.release();
+    c->dSceneDepth.release(); c->dOrderOf.release(); c->dTris.release(); c->dScene.release();
     if (c->linkUp && c->linkUpIpc) cudaIpcCloseMemHandle(c->linkUp);
     if (c->linkDown && c->linkDownIpc) cudaIpcCloseMemHandle(c->linkDown);
     if (c->linkOwn) cudaFree(c->linkOwn);
@@ -660,6 +686,75 @@ int vpe_set_light_depth_map(VpeContext* c, const float* depth01) {
     CUDA_TRY(c, cudaMemcpy(c->dDepth.p, depth01, n * sizeof(float), cudaMemcpyHostToDevice));
     c->depthSet = true;
     return VPE_OK;
+}
+
+int vpe_render_light_depth_map(VpeContext* c, const float* tris, int numTriangles) {
+    if (!c || (!tris && numTriangles > 0) || numTriangles < 0) return fail(c, VPE_E_INVALID_ARG, "bad triangle list");
+    if (!c->lightSet) return fail(c, VPE_E_NOT_READY, "vpe_set_light has not been called");
+    cudaSetDevice(c->device);
+    const GridParams& g = c->g;
+    DepthRasterParams p;
+    p.W2LC = c->w2lc;
+    p.r = (float)g.NX * g.s * 0.5f; p.t = (float)g.NY * g.s * 0.5f;  // VPR.cs:340
+    p.zn = c->cfg.lightNear; p.zf = c->cfg.lightFar;
+    p.W = g.NX * g.N; p.H = g.NY * g.N;
+    const size_t n = (size_t)p.W * p.H;
+    CUDA_TRY(c, c->dDepth.ensure(n));
+    CUDA_TRY(c, c->dTris.ensure((size_t)std::max(numTriangles, 1) * 9));
+    if (numTriangles > 0)
+        CUDA_TRY(c, cudaMemcpyAsync(c->dTris.p, tris, sizeof(float) * 9 * (size_t)numTriangles, cudaMemcpyHostToDevice, c->stream));
+    k_fill_value<<<std::min(div_up(n, 256), 148 * 8), 256, 0, c->stream>>>(c->dDepth.p, n, 1.0f);  // CameraClearFlags.Depth
+    if (numTriangles > 0)
+        k_raster_depth<<<std::min(numTriangles, 148 * 16), 256, 0, c->stream>>>(p, c->dTris.p, numTriangles, reinterpret_cast<unsigned*>(c->dDepth.p));
+    CUDA_TRY(c, cudaGetLastError());
+    c->depthSet = true;
+    return sync_stream(c);
+}
+
+int vpe_read_light_depth_map(VpeContext* c, float* depth01) {
+    if (!c || !depth01) return VPE_E_INVALID_ARG;
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    const size_t n = (size_t)c->g.NX * c->g.N * c->g.NY * c->g.N;
+    if (!c->depthSet) {
+        for (size_t i = 0; i < n; i++) depth01[i] = 1.0f;
+        return VPE_OK;
+    }
+    CUDA_TRY(c, cudaMemcpy(depth01, c->dDepth.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return VPE_OK;
+}
+
+int vpe_set_march_options(VpeContext* c, const VpeMarchOptions* o) {
+    if (!c || !o) return VPE_E_INVALID_ARG;
+    if (o->targetFormat < 0 || o->targetFormat > 1 || o->debugMode < 0 || o->debugMode > 3) return fail(c, VPE_E_INVALID_ARG, "bad march option");
+    if (o->sceneDepth && (o->sceneWidth < 1 || o->sceneHeight < 1)) return fail(c, VPE_E_INVALID_ARG, "bad scene depth size");
+    cudaSetDevice(c->device);
+    c->targetFormat = o->targetFormat;
+    c->debugMode = o->debugMode;
+    c->sceneDepthSet = false;
+    if (o->sceneDepth) {
+        const size_t n = (size_t)o->sceneWidth * o->sceneHeight;
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        CUDA_TRY(c, c->dSceneDepth.ensure(n));
+        CUDA_TRY(c, cudaMemcpy(c->dSceneDepth.p, o->sceneDepth, n * sizeof(float), cudaMemcpyHostToDevice));
+        c->sceneW = o->sceneWidth; c->sceneH = o->sceneHeight;
+        c->sceneDepthSet = true;
+    }
+    return VPE_OK;
+}
+
+int vpe_composite_scene(VpeContext* c, const float* particles, float* scene, int numPixels, int targetFormat) {
+    if (!c || !particles || !scene || numPixels < 0 || targetFormat < 0 || targetFormat > 1) return fail(c, VPE_E_INVALID_ARG, "bad argument");
+    if (numPixels == 0) return VPE_OK;
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, c->dImage.ensure((size_t)numPixels));
+    CUDA_TRY(c, c->dScene.ensure((size_t)numPixels));
+    CUDA_TRY(c, cudaMemcpyAsync(c->dImage.p, particles, sizeof(float4) * (size_t)numPixels, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->dScene.p, scene, sizeof(float4) * (size_t)numPixels, cudaMemcpyHostToDevice, c->stream));
+    k_composite_scene<<<div_up(numPixels, 256), 256, 0, c->stream>>>(c->dImage.p, c->dScene.p, numPixels, targetFormat);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(scene, c->dScene.p, sizeof(float4) * (size_t)numPixels, cudaMemcpyDeviceToHost, c->stream));
+    return sync_stream(c);
 }
 
 int vpe_set_stream(VpeContext* c, void* cudaStream) {

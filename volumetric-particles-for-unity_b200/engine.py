@@ -150,6 +150,39 @@ class Engine:
         assert d.shape == (self.grid[1] * self.N, self.grid[0] * self.N)
         self._check(self.lib.vpe_set_light_depth_map(self._ctx, d.ctypes.data))
 
+    # -- around the path ---------------------------------------------------------
+    def render_light_depth_map(self, triangles):
+        """≙ lightCamera.RenderWithShader(generateLightDepthMapShader) (VPR.cs:184): triangles is
+        (n, 3, 3) world-space vertices, Unity winding (clockwise = front)."""
+        t = np.ascontiguousarray(triangles, dtype=np.float32).reshape(-1, 9)
+        self._check(self.lib.vpe_render_light_depth_map(self._ctx, t.ctypes.data if t.shape[0] else None, t.shape[0]))
+
+    def read_light_depth_map(self):
+        out = np.empty((self.grid[1] * self.N, self.grid[0] * self.N), dtype=np.float32)
+        self._check(self.lib.vpe_read_light_depth_map(self._ctx, out.ctypes.data))
+        return out
+
+    def set_march_options(self, target_format=0, debug_mode=0, scene_depth=None):
+        """target_format 1 = UNORM8 target like particlesRT (VPR.cs:228); debug_mode 1/2/3 = draw order /
+        blend function / sample-count views (March.shader:170-181,283-299); scene_depth = (H, W) eye-space
+        depths of the opaque scene (≙ ZTest Less against mainSceneRT.depthBuffer, VPR.cs:204)."""
+        o = _abi.VpeMarchOptions()
+        o.targetFormat, o.debugMode = int(target_format), int(debug_mode)
+        keep = None
+        if scene_depth is not None:
+            keep = np.ascontiguousarray(scene_depth, dtype=np.float32)
+            o.sceneDepth = keep.ctypes.data
+            o.sceneHeight, o.sceneWidth = keep.shape
+        self._check(self.lib.vpe_set_march_options(self._ctx, C.byref(o)))
+
+    def composite_scene(self, particles_rgba, scene_rgba, target_format=0):
+        """≙ Graphics.Blit(particlesRT, mainSceneRT, matBlendParticles) (VPR.cs:210). Returns the new scene."""
+        p = np.ascontiguousarray(particles_rgba, dtype=np.float32)
+        sc = np.array(scene_rgba, dtype=np.float32, order="C", copy=True)
+        assert p.shape == sc.shape and p.shape[-1] == 4
+        self._check(self.lib.vpe_composite_scene(self._ctx, p.ctypes.data, sc.ctypes.data, p.size // 4, int(target_format)))
+        return sc
+
     # -- hot path, host buffers -----------------------------------------------------------
     def fill(self, particles, emitter):
         p = _particles(particles)
