@@ -41,6 +41,7 @@ struct VpeApi {
     VPE_FN(vpe_set_displacement_cubemap) VPE_FN(vpe_set_light_depth_map) VPE_FN(vpe_fill) VPE_FN(vpe_march)
     VPE_FN(vpe_march_pixels) VPE_FN(vpe_get_stats) VPE_FN(vpe_last_error) VPE_FN(vpe_abi_version) VPE_FN(vpe_backend)
     VPE_FN(vpe_read_brick) VPE_FN(vpe_read_light_sheet)
+    VPE_FN(vpe_render_light_depth_map) VPE_FN(vpe_set_march_options) VPE_FN(vpe_composite_scene)
 #undef VPE_FN
     bool load(const char* path, std::string* why) {
         handle = dlopen(path, RTLD_NOW | RTLD_LOCAL);
@@ -52,6 +53,7 @@ struct VpeApi {
         VPE_BIND(vpe_set_displacement_cubemap) VPE_BIND(vpe_set_light_depth_map) VPE_BIND(vpe_fill) VPE_BIND(vpe_march)
         VPE_BIND(vpe_march_pixels) VPE_BIND(vpe_get_stats) VPE_BIND(vpe_last_error) VPE_BIND(vpe_abi_version) VPE_BIND(vpe_backend)
         VPE_BIND(vpe_read_brick) VPE_BIND(vpe_read_light_sheet)
+        VPE_BIND(vpe_render_light_depth_map) VPE_BIND(vpe_set_march_options) VPE_BIND(vpe_composite_scene)
 #undef VPE_BIND
         if (vpe_abi_version() != VPE_ABI_VERSION) { if (why) *why = "ABI version mismatch"; return false; }
         return true;
@@ -106,6 +108,14 @@ public:
 
     // lightDepthMap (VPR.cs:184,274): depth01 = (NY*N) x (NX*N) floats or nullptr for "no occluders".
     int SetLightDepthMap(const float* depth01) { return check(api_.vpe_set_light_depth_map(ctx_, depth01)); }
+    // lightCamera.RenderWithShader(generateLightDepthMapShader), VPR.cs:184: occluder triangles in world space
+    int RenderLightDepthMap(const float* trianglesWorld, int numTriangles) { return check(api_.vpe_render_light_depth_map(ctx_, trianglesWorld, numTriangles)); }
+    // debug views (VPR.cs:96-99,744-761), 8-bit particlesRT (VPR.cs:228), scene depth test (VPR.cs:204)
+    int SetMarchOptions(const VpeMarchOptions& o) { return check(api_.vpe_set_march_options(ctx_, &o)); }
+    // Graphics.Blit(particlesRT, mainSceneRT, matBlendParticles), VPR.cs:210
+    int CompositeParticles(const float* particlesRT, float* mainSceneRT, int numPixels, int targetFormat = 0) {
+        return check(api_.vpe_composite_scene(ctx_, particlesRT, mainSceneRT, numPixels, targetFormat));
+    }
 
     // VPR.cs:181-220. particles = ParticleSystem.GetParticles(); rgba = particlesRT as float4 (H*W*4).
     int OnPostRender(const VpeParticle* particles, int numParticles, const VpeCamera& camera, float* rgba) {

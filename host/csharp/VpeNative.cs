@@ -64,6 +64,16 @@ namespace MetavoxelEngine.Native
         public float fillKernelMs, marchKernelMs;
     }
 
+    /// VpeMarchOptions of include/vpe.h: UNORM8 target (particlesRT is ARGB32, VPR.cs:228), the debug views of
+    /// SetRaymarchPassConstants (VPR.cs:744-761), the scene depth of mainSceneRT (VPR.cs:204) as eye-space floats.
+    [StructLayout(LayoutKind.Sequential)]
+    public struct VpeMarchOptions
+    {
+        public int targetFormat, debugMode;
+        public IntPtr sceneDepth;          // pinned float[sceneHeight * sceneWidth] or IntPtr.Zero
+        public int sceneWidth, sceneHeight;
+    }
+
     public static class Vpe
     {
         const string Lib = "vpe_cuda";       // libvpe_cuda.so next to the player / in Assets/Plugins/x86_64
@@ -77,6 +87,10 @@ namespace MetavoxelEngine.Native
         [DllImport(Lib)] public static extern int vpe_set_light_depth_map(IntPtr ctx, float[] depth01);
         [DllImport(Lib)] public static extern int vpe_fill(IntPtr ctx, [In] VpeParticle[] particles, int n, ref VpeTransform emitter);
         [DllImport(Lib)] public static extern int vpe_march(IntPtr ctx, ref VpeCamera cam, [Out] float[] rgba, [Out] int[] samples);
+        // the rest of the frame (VPR.cs:184,204,210)
+        [DllImport(Lib)] public static extern int vpe_render_light_depth_map(IntPtr ctx, [In] float[] trianglesWorld, int numTriangles);
+        [DllImport(Lib)] public static extern int vpe_set_march_options(IntPtr ctx, ref VpeMarchOptions options);
+        [DllImport(Lib)] public static extern int vpe_composite_scene(IntPtr ctx, [In] float[] particlesRgba, [In, Out] float[] sceneRgba, int numPixels, int targetFormat);
         [DllImport(Lib)] public static extern int vpe_get_stats(IntPtr ctx, out VpeStats stats);
         [DllImport(Lib)] public static extern IntPtr vpe_last_error(IntPtr ctx);
         [DllImport(Lib)] public static extern int vpe_abi_version();

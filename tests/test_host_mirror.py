@@ -47,6 +47,20 @@ def check_frame_structure(lib):
     r.SetRayMarchSteps(64)
     _, samples64 = r.RenderMetavoxels(sc["camera"], show_samples=True)
     assert 3.5 < samples64.sum() / samples16.sum() < 4.5
+    # the rest of the frame (VPR.cs:184,204,210): occluders seen from the light, scene depth, blend onto the scene
+    import frame_scenes
+    h, w = sc["camera"]["height"], sc["camera"]["width"]
+    scene_rt = np.zeros((h, w, 4), dtype=np.float32)
+    scene_rt[..., 2] = 0.5
+    full = r.OnPostRender(moved, sc["camera"], occluders=frame_scenes.occluders(sc), mainSceneRT=scene_rt,
+                          sceneDepth=frame_scenes.scene_depth(sc))
+    assert full.shape == (h, w, 4) and (full[:h // 4, :w // 4, 2] == 0.5).all()   # hidden behind the scene: untouched
+    assert full[..., 0].sum() < r.engine.composite_scene(f3, scene_rt)[..., 0].sum()   # shadowed and partly hidden
+    r.ShowRayMarchBlendFunc(True)
+    view = r.RenderMetavoxels(sc["camera"])
+    assert set(np.unique(view)) <= {0.0, 0.5, 1.0}
+    r.ShowRayMarchBlendFunc(False)
+    r.engine.render_light_depth_map(np.zeros((0, 3, 3), dtype=np.float32))
     r.SetGridScale(1.5)                                      # re-places the metavoxels (VPR.cs:1059-1063)
     assert np.allclose(r.engine.read_metavoxel_position(5, 4, 4) - r.engine.read_metavoxel_position(4, 4, 4), [1.5, 0, 0], atol=1e-5)
     return f0

@@ -36,6 +36,11 @@ class VolumetricParticleRenderer:
         self.fadeOutParticles = False
         self.opacityFactor = 0.04
         self.softParticleStepDistance = 20
+        # debug views (VPR.cs:96-99) and the render target (particlesRT is ARGB32, VPR.cs:228; float by default here)
+        self.bShowRayMarchSamplesPerPixel = False
+        self.bShowMetavoxelDrawOrder = False
+        self.bShowRayMarchBlendFunc = False
+        self.particlesRT_8bit = False
         # counters (VPR.cs:124-125)
         self.numParticlesEmitted = 0
         self.numMetavoxelsCovered = 0
@@ -52,14 +57,22 @@ class VolumetricParticleRenderer:
         self._frameCount = 0
         self.UpdateMetavoxelPositions()
 
-    def OnPostRender(self, particles, camera):
-        """VPR.cs:181-220: returns particlesRT for this frame."""
+    def OnPostRender(self, particles, camera, occluders=None, mainSceneRT=None, sceneDepth=None):
+        """VPR.cs:181-220. Returns particlesRT for this frame, or, when mainSceneRT (H x W x 4 scene colour) is
+        given, the scene with the particles blended onto it (VPR.cs:210). occluders: (n, 3, 3) world-space
+        triangles of the Default layer seen by the light camera (VPR.cs:184); sceneDepth: (H, W) eye-space
+        depth of mainSceneRT.depthBuffer (VPR.cs:204)."""
+        if occluders is not None:
+            self._engine.render_light_depth_map(occluders)   # VPR.cs:184, every frame
         if self.updateInterval < 1 or self._frameCount % self.updateInterval == 0:  # VPR.cs:186
             self._push_config()
             self.UpdateMetavoxelPositions()        # VPR.cs:188-195
             self.FillMetavoxels(particles)         # VPR.cs:197-198
         self._frameCount += 1
-        return self.RenderMetavoxels(camera)       # VPR.cs:207
+        particlesRT = self.RenderMetavoxels(camera, sceneDepth=sceneDepth)   # VPR.cs:204-207
+        if mainSceneRT is None:
+            return particlesRT
+        return self._engine.composite_scene(particlesRT, mainSceneRT, 1 if self.particlesRT_8bit else 0)  # VPR.cs:210
 
     # -- the two dispatch entry points ----------------------------------------------------------
     def UpdateMetavoxelPositions(self):
@@ -76,9 +89,12 @@ class VolumetricParticleRenderer:
         st = self._engine.stats()
         self.numParticlesEmitted, self.numMetavoxelsCovered = st["numParticles"], st["numMetavoxelsCovered"]
 
-    def RenderMetavoxels(self, camera, show_samples=False):
-        """VPR.cs:637-713. show_samples ≙ bShowRayMarchSamplesPerPixel: also return the per-pixel count."""
+    def RenderMetavoxels(self, camera, show_samples=False, sceneDepth=None):
+        """VPR.cs:637-713 (+ SetRaymarchPassConstants' debug flags, VPR.cs:744-761). show_samples: also return
+        the per-pixel ray-sample count."""
         self._push_config()
+        debug = 1 if self.bShowMetavoxelDrawOrder else 2 if self.bShowRayMarchBlendFunc else 3 if self.bShowRayMarchSamplesPerPixel else 0
+        self._engine.set_march_options(target_format=1 if self.particlesRT_8bit else 0, debug_mode=debug, scene_depth=sceneDepth)
         rgba, samples = self._engine.march(camera, want_samples=show_samples)
         return (rgba, samples) if show_samples else rgba
 
@@ -101,6 +117,15 @@ class VolumetricParticleRenderer:
 
     def SetParticleOpacityFactor(self, f):
         self.opacityFactor = float(f)
+
+    def ShowRayMarchSamplesPerPixel(self, show):   # VPR.cs:1091-1094
+        self.bShowRayMarchSamplesPerPixel = bool(show)
+
+    def ShowMetavoxelDrawOrder(self, show):        # VPR.cs:1096-1099
+        self.bShowMetavoxelDrawOrder = bool(show)
+
+    def ShowRayMarchBlendFunc(self, show):
+        self.bShowRayMarchBlendFunc = bool(show)
 
     def SetUpdateInterval(self, interval):
         self.updateInterval = int(interval)
