@@ -84,6 +84,7 @@ struct MarchParams {
     int maxSamplesPerMv;         // hang guard: (int)(sqrt(3)/stepSize) + 2
     int wrap;                    // border == 0: repeat addressing can trigger (VPR.cs:770)
     int tileLog2W;               // warp pixel tile = 2^tileLog2W x (32 >> tileLog2W)
+    int blockYBase;              // first row of CTAs of this launch (the host path launches the image in bands)
     int rowStride;               // = GridParams::rowStride
     int gray;                    // layout of the bricks being marched (GridParams::gray at fill time)
     int targetFormat, debugMode; // VpeMarchOptions (legacy kernel only)

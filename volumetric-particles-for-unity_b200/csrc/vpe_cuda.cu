@@ -88,6 +88,10 @@ struct VpeContext {
     bool linkUpIpc = false, linkDownIpc = false;
     int linkBlocks = 0;
     unsigned linkEpoch = 0;
+    // host-path march: bands on two auxiliary streams, each copied home as soon as it is done
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // two compute streams + one copy stream
+    cudaEvent_t evFork = nullptr, evJoin[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t evBand[32] = {};
     // around the path: light camera, march options
     Affine w2lc;                     // lightCamera.transform.worldToLocalMatrix (VPR.cs:365-366)
     int targetFormat = 0, debugMode = 0;
@@ -351,8 +355,17 @@ struct SortData {  // ≙ MetavoxelSortData, VPR.cs:43-62
     float distance;
 };
 
+// Host destination of a full-image march: when given (and pinned), the image is marched in bands of CTA rows on
+// two auxiliary streams and every band is copied to the host as soon as it is done, so that the device-to-host
+// copy of the image overlaps the march instead of following it.
+struct HostImage {
+    float* rgba = nullptr;
+    int32_t* samples = nullptr;
+    bool copied = false;   // out: the bands have been copied (the caller must not copy again)
+};
+
 int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nPixels, float4* rgbaDev, float4* underDev,
-               int* samplesDev, bool partial, unsigned* footprint = nullptr) {
+               int* samplesDev, bool partial, unsigned* footprint = nullptr, HostImage* host = nullptr) {
     GridParams& g = c->g;
     const VpeConfig& k = c->cfg;
     if (cam->width < 1 || cam->height < 1) return fail(c, VPE_E_INVALID_ARG, "bad image size");
@@ -458,14 +471,44 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
         m.tileLog2W = lw;
     }
     dim3 grid, block(128);
+    int ctaRows = 1;  // image rows per row of CTAs
     if (pixelsDev) grid = dim3(div_up(nPixels, 128));
     else {
         const int lw = m.tileLog2W, tw = 1 << lw, th = 32 >> lw;
         const int cw = lw >= 4 ? tw : (lw <= 1 ? 4 * tw : 2 * tw), ch = lw >= 4 ? 4 * th : (lw <= 1 ? th : 2 * th);
         grid = dim3(div_up(cam->width, cw), div_up(cam->height, ch));
+        ctaRows = ch;
+    }
+    // bands (host path): only worth it for a large image going to pinned memory
+    int numBands = 1;
+    if (host && host->rgba && !pixelsDev && !partial && !footprint && (int)grid.y >= 32 && m.numPixels >= (1 << 19) && !getenv("VPE_MARCH_NO_BANDS")) {
+        cudaPointerAttributes at;
+        const char* nb = getenv("VPE_MARCH_BANDS");
+        if (cudaPointerGetAttributes(&at, host->rgba) == cudaSuccess && at.type == cudaMemoryTypeHost)
+            numBands = nb ? std::min(std::max(atoi(nb), 1), 32) : 6;  // measured on cfg3: 4-8 bands 7.40-7.46 ms, 16 bands 8.7, one launch + one copy 7.86
+        else cudaGetLastError();
+        if (numBands > 1 && host->samples) {
+            if (!(cudaPointerGetAttributes(&at, host->samples) == cudaSuccess && at.type == cudaMemoryTypeHost)) { cudaGetLastError(); numBands = 1; }
+        }
+        if (numBands > 1 && !c->aux[0]) {
+            bool ok = cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming) == cudaSuccess;
+            for (int i = 0; i < 3; i++)
+                ok = ok && cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&c->evJoin[i], cudaEventDisableTiming) == cudaSuccess;
+            for (int i = 0; i < 32; i++) ok = ok && cudaEventCreateWithFlags(&c->evBand[i], cudaEventDisableTiming) == cudaSuccess;
+            if (!ok) { cudaGetLastError(); numBands = 1; }
+        }
     }
     CUDA_TRY(c, cudaEventRecord(c->evMarchK0, c->stream));
-    if (m.numPixels > 0) {
+    if (numBands > 1) {
+        CUDA_TRY(c, cudaEventRecord(c->evFork, c->stream));
+        for (int i = 0; i < 3; i++) CUDA_TRY(c, cudaStreamWaitEvent(c->aux[i], c->evFork, 0));
+    }
+    const dim3 fullGrid = grid;
+    for (int band = 0; band < numBands && m.numPixels > 0; band++) {
+        cudaStream_t st = numBands > 1 ? c->aux[band & 1] : c->stream;
+        const int by0 = (int)((long long)band * fullGrid.y / numBands), by1 = (int)((long long)(band + 1) * fullGrid.y / numBands);
+        if (numBands > 1) { grid = dim3(fullGrid.x, by1 - by0); m.blockYBase = by0; }
         const bool legacy = m.wrap || optionsActive || getenv("VPE_MARCH_LEGACY");
         const bool gray = c->bricksGray;  // the layout the fill wrote (z-paired grey texels or half4)
         // k_march_merged trades divergence (26.6 instead of 22.6 active lanes) for L1 bank conflicts (lanes in
@@ -473,10 +516,10 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
         const bool merged = getenv("VPE_MARCH_MERGED") != nullptr;
 #define VPE_LAUNCH_MARCH3(KERNEL, ...)                                                                  \
     do {                                                                                                \
-        if (skip && gray) KERNEL<__VA_ARGS__, true, true, PAD_><<<grid, block, 0, c->stream>>>(g, m, a); \
-        else if (skip) KERNEL<__VA_ARGS__, true, false, PAD_><<<grid, block, 0, c->stream>>>(g, m, a);   \
-        else if (gray) KERNEL<__VA_ARGS__, false, true, PAD_><<<grid, block, 0, c->stream>>>(g, m, a);   \
-        else KERNEL<__VA_ARGS__, false, false, PAD_><<<grid, block, 0, c->stream>>>(g, m, a);            \
+        if (skip && gray) KERNEL<__VA_ARGS__, true, true, PAD_><<<grid, block, 0, st>>>(g, m, a); \
+        else if (skip) KERNEL<__VA_ARGS__, true, false, PAD_><<<grid, block, 0, st>>>(g, m, a);   \
+        else if (gray) KERNEL<__VA_ARGS__, false, true, PAD_><<<grid, block, 0, st>>>(g, m, a);   \
+        else KERNEL<__VA_ARGS__, false, false, PAD_><<<grid, block, 0, st>>>(g, m, a);            \
     } while (0)
 #define VPE_LAUNCH_MARCH2(NT, PAD)                           \
     do {                                                     \
@@ -489,17 +532,32 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
         if (m.rowStride != g.N) VPE_LAUNCH_MARCH2(NT, true);  \
         else VPE_LAUNCH_MARCH2(NT, false);       \
     } while (0)
-        if (footprint) k_march<-1, true, false, false, false><<<grid, block, 0, c->stream>>>(g, m, a);
-        else if (legacy) k_march<-1, false, false, false, false><<<grid, block, 0, c->stream>>>(g, m, a);
+        if (footprint) k_march<-1, true, false, false, false><<<grid, block, 0, st>>>(g, m, a);
+        else if (legacy) k_march<-1, false, false, false, false><<<grid, block, 0, st>>>(g, m, a);
         else if (g.N == 32) VPE_LAUNCH_MARCH(32);
         else if (g.N == 64) VPE_LAUNCH_MARCH(64);
         else VPE_LAUNCH_MARCH(0);
 #undef VPE_LAUNCH_MARCH2
 #undef VPE_LAUNCH_MARCH3
 #undef VPE_LAUNCH_MARCH
+        if (numBands > 1) {  // this band's rows go home (copy stream) while the next bands are marched
+            const int r0 = by0 * ctaRows, r1 = std::min(cam->height, by1 * ctaRows);
+            const size_t off = (size_t)r0 * cam->width, cnt = (size_t)(r1 - r0) * cam->width;
+            CUDA_TRY(c, cudaEventRecord(c->evBand[band], st));
+            CUDA_TRY(c, cudaStreamWaitEvent(c->aux[2], c->evBand[band], 0));
+            CUDA_TRY(c, cudaMemcpyAsync(host->rgba + off * 4, rgbaDev + off, cnt * sizeof(float4), cudaMemcpyDeviceToHost, c->aux[2]));
+            if (host->samples && samplesDev) CUDA_TRY(c, cudaMemcpyAsync(host->samples + off, samplesDev + off, cnt * sizeof(int), cudaMemcpyDeviceToHost, c->aux[2]));
+        }
+    }
+    if (numBands > 1) {
+        for (int i = 0; i < 3; i++) {
+            CUDA_TRY(c, cudaEventRecord(c->evJoin[i], c->aux[i]));
+            CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->evJoin[i], 0));
+        }
+        host->copied = true;
     }
     CUDA_TRY(c, cudaEventRecord(c->evMarchK1, c->stream));
-    c->stats.marchLaunches = 2;
+    c->stats.marchLaunches = 1 + numBands;
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaMemcpyAsync(c->hTotalSamples, c->dTotalSamples.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaEventRecord(c->evMarch1, c->stream));
@@ -599,6 +657,13 @@ int vpe_destroy(VpeContext* c) {
     c->dRank.release(); c->dPixels.release(); c->dSamples.release(); c->dImage.release(); c->dImage2.release();
     c->dTotalSamples.release(); c->dParts.release();
     c->dSceneDepth.release(); c->dOrderOf.release(); c->dTris.release(); c->dScene.release();
+    for (int i = 0; i < 3; i++) {
+        if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
+        if (c->evJoin[i]) cudaEventDestroy(c->evJoin[i]);
+    }
+    for (int i = 0; i < 32; i++)
+        if (c->evBand[i]) cudaEventDestroy(c->evBand[i]);
+    if (c->evFork) cudaEventDestroy(c->evFork);
     if (c->linkUp && c->linkUpIpc) cudaIpcCloseMemHandle(c->linkUp);
     if (c->linkDown && c->linkDownIpc) cudaIpcCloseMemHandle(c->linkDown);
     if (c->linkOwn) cudaFree(c->linkOwn);
@@ -939,10 +1004,15 @@ int vpe_march(VpeContext* c, const VpeCamera* cam, float* rgba, int32_t* samples
     const size_t np = (size_t)cam->width * cam->height;
     CUDA_TRY(c, c->dImage.ensure(np));
     if (samples) CUDA_TRY(c, c->dSamples.ensure(np));
-    rc = march_impl(c, cam, nullptr, 0, c->dImage.p, nullptr, samples ? c->dSamples.p : nullptr, false);
+    HostImage host;
+    host.rgba = rgba;
+    host.samples = samples;
+    rc = march_impl(c, cam, nullptr, 0, c->dImage.p, nullptr, samples ? c->dSamples.p : nullptr, false, nullptr, &host);
     if (rc) return rc;
-    CUDA_TRY(c, cudaMemcpyAsync(rgba, c->dImage.p, np * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-    if (samples) CUDA_TRY(c, cudaMemcpyAsync(samples, c->dSamples.p, np * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (!host.copied) {
+        CUDA_TRY(c, cudaMemcpyAsync(rgba, c->dImage.p, np * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+        if (samples) CUDA_TRY(c, cudaMemcpyAsync(samples, c->dSamples.p, np * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    }
     return sync_stream(c);
 }
 
