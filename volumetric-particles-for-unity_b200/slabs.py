@@ -282,8 +282,20 @@ class CudaSlabEngine:
             return False
         up = everyone[rank - 1][1] if rank > 0 else None
         down = everyone[rank + 1][1] if rank < world - 1 else None
-        self.eng.sheet_link_connect(up, down)
-        dist.barrier()
+        ok = True
+        try:
+            self.eng.sheet_link_connect(up, down)   # cudaIpcOpenMemHandle + peer access
+        except Exception:
+            ok = False
+        # the link is used only if every rank could map its neighbours (all ranks must take the same path)
+        results = [None] * world
+        dist.all_gather_object(results, ok)
+        if not all(results):
+            try:
+                self.eng.sheet_link_connect(None, None)
+            except Exception:
+                pass
+            return False
         return True
 
     def fill_sweep_linked(self):
