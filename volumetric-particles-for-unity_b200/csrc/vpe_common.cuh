@@ -47,13 +47,16 @@ VPE_HD F3 mv_center(const GridParams& g, int x, int y, int z) {
 }
 
 // per-particle fill input (≙ DisplacedParticle, VPR.cs:34-40: only mWorldToLocal and mOpacity are
-// read by the shader, Fill.shader:169,174). 64 bytes so a warp-uniform read is four LDS.128.
+// read by the shader, Fill.shader:169,174). 80 bytes so a warp-uniform read is five LDS.128.
 struct __align__(16) ParticleFill {
     float m[3][4];
     float opacity;
-    float rejectAbove;  // 0.25 + error band of the fused pre-test (k_particle_setup); see k_fill_columns
+    float rejectAbove;  // 0.25 + error band of the fused evaluations (k_particle_setup); see k_fill_columns
     float pad[2];
+    float dq[3];        // mWorldToLocal's 3x3 block times the light step: particle-space motion per slice
+    float dqLen2;       // dot(dq, dq)
 };
+constexpr int PARTICLE_FILL_VEC4 = 5;  // sizeof(ParticleFill) / 16
 
 // per-particle binning record
 struct ParticleBin {
