@@ -131,6 +131,52 @@ def test_linked_sweep_two_contexts_on_one_gpu():
     check_volume()
 
 
+@pytest.mark.parametrize("n_vox,grid,ranks_z", [(64, (2, 2, 4), [(0, 1), (1, 4)]), (12, (3, 3, 5), [(0, 2), (2, 3), (3, 5)]),
+                                               (32, (2, 3, 3), [(0, 1), (1, 2), (2, 3)])])
+def test_linked_sweep_other_brick_sizes_and_three_slabs(n_vox, grid, ranks_z):
+    """The linked sweep with 64^3 bricks (16 blocks of voxel columns per metavoxel column), with a brick edge that is
+    not a multiple of the 8x4 warp tile (idle lanes must still take part in the block's hand-shake) and through a chain
+    of three contexts: bricks and sheet bit-identical to the single-context fill."""
+    import torch
+    sc = scenes.make_scene("cfg1", image=(48, 48))
+    sc["grid"], sc["numVoxels"] = tuple(grid), n_vox
+    rng = np.random.default_rng(77)
+    half = (np.asarray(grid, dtype=np.float64) / 2 - 0.6) * sc["mvScale"]
+    p = scenes.make_particles_uniform(rng, 14, 8, sc["mvScale"])
+    p[:, 0:3] = scenes.quat_rotate(scenes.LIGHT_ROTATION, rng.uniform(-half, half, size=(14, 3))).astype(np.float32)
+    sc["particles"] = p
+    one = vpe_b200.engine_for_scene(None, sc)
+    scenes.apply_scene(one, sc)
+    one.fill(sc["particles"], sc["emitter"])
+    world = len(ranks_z)
+    ranks = [slabs.CudaSlabEngine(sc, r, world, 0) for r in range(world)]
+    for e, (z0, z1) in zip(ranks, ranks_z):
+        e.set_slab(z0, z1)
+    ptrs = [e.eng.sheet_link_create()[1] for e in ranks]
+    for r, e in enumerate(ranks):
+        e.eng.sheet_link_connect(ptrs[r - 1] if r > 0 else None, ptrs[r + 1] if r < world - 1 else None)
+    for it in range(2):
+        for e in ranks:
+            e.fill_prepare(sc["particles"], sc["emitter"])
+            e.fill_density()
+        for e in ranks:
+            e.fill_sweep_linked()
+        torch.cuda.synchronize()
+        assert all(e.eng.sheet_link_timeouts() == 0 for e in ranks)
+    assert np.array_equal(ranks[-1].eng.read_light_sheet(), one.read_light_sheet())
+    cov = 0
+    for z in range(grid[2]):
+        owner = next(e for e, (z0, z1) in zip(ranks, ranks_z) if z0 <= z < z1)
+        for y in range(grid[1]):
+            for x in range(grid[0]):
+                a, b = one.read_brick(x, y, z), owner.eng.read_brick(x, y, z)
+                assert (a is None) == (b is None)
+                if a is not None:
+                    cov += 1
+                    assert np.array_equal(a, b)
+    assert cov == one.stats()["numMetavoxelsCovered"] > 0
+
+
 def test_linked_sweep_reports_a_missing_peer(monkeypatch):
     """A downstream rank whose upstream never arrives gives up after the spin limit and says so; it does
     not hang the GPU."""

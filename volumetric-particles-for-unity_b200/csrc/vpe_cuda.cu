@@ -4,9 +4,12 @@
 //   vpe_fill   ≙ BinParticlesToMetavoxels + FillMetavoxels   (VPR.cs:397-520)
 //   vpe_march  ≙ RenderMetavoxels                            (VPR.cs:637-713)
 // but instead of one draw call per metavoxel it issues a handful of launches: particle set-up and
-// counting-sort binning, then one fill launch per light-axis slice (the only true dependency), then
-// one march launch for the whole image that walks the metavoxels per ray in the reference's
-// submission order.  There is NO CPU fallback: every entry point that computes runs on the GPU.
+// counting-sort binning, then ONE fill launch in which every voxel column walks all light-axis slices
+// (the light dependency is carried in a register), then one march launch for the whole image that walks
+// the metavoxels per ray in the reference's submission order (the host-buffer path launches the image in
+// bands so that the copy home overlaps).  Multi-GPU entry points split the fill at the light sheet and
+// hand it over through peer memory (vpe_sheet_link_*).  There is NO CPU fallback: every entry point that
+// computes runs on the GPU.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -511,8 +514,8 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
         if (numBands > 1) { grid = dim3(fullGrid.x, by1 - by0); m.blockYBase = by0; }
         const bool legacy = m.wrap || optionsActive || getenv("VPE_MARCH_LEGACY");
         const bool gray = c->bricksGray;  // the layout the fill wrote (z-paired grey texels or half4)
-        // k_march_merged trades divergence (26.6 instead of 22.6 active lanes) for L1 bank conflicts (lanes in
-        // different bricks): 9.2 vs 8.9 ms on cfg3 with 8-byte texels (profiles/). Opt-in until the texel fetch is cheaper.
+        // k_march_merged trades divergence (26.6 instead of 23 active lanes) for a longer loop with lanes in
+        // different bricks: 7.75 vs 7.2 ms on cfg3 (profiles/r01_final_summary.md). Opt-in.
         const bool merged = getenv("VPE_MARCH_MERGED") != nullptr;
 #define VPE_LAUNCH_MARCH3(KERNEL, ...)                                                                  \
     do {                                                                                                \
