@@ -218,6 +218,19 @@ int vpe_sheet_link_status(VpeContext* ctx, int* timeouts);
  * under = its slices > zBoundary composited front-to-back (phase 2, VPR.cs:688-711). */
 int vpe_march_partial_device(VpeContext* ctx, const VpeCamera* cam, float* over_dev,
                              float* under_dev, int32_t* samples_dev);
+/* The same with the exchange of the partial images inside the march kernel (CUDA library only): every rank owns
+ * a receive buffer for the image rows it composites (rows [q*per, (q+1)*per), per = ceil(height / world));
+ * vpe_image_link_create allocates it (64-byte CUDA IPC handle and/or device pointer out), vpe_image_link_connect
+ * maps all ranks' buffers (peers[q] = rank q's handle or pointer to its device pointer; peers[rank] is ignored).
+ * vpe_march_linked marches the slab and stores every pixel's two partials straight into the receive buffer of the
+ * rank that owns its row (peer stores over NVLink), then raises this rank's flag on every rank;
+ * vpe_composite_linked waits for all ranks' flags and composites this rank's band (per*width*4 floats, device) in
+ * the reference's order. No collective is involved. All ranks call both once per frame. */
+int vpe_image_link_create(VpeContext* ctx, int world, int rank, int width, int height, void* ipcHandle64, void** devPtr);
+int vpe_image_link_connect(VpeContext* ctx, const void* const* peers, int handlesAreIpc);
+int vpe_march_linked(VpeContext* ctx, const VpeCamera* cam, int32_t* samples_dev);
+int vpe_composite_linked(VpeContext* ctx, float* band_rgba_dev);
+int vpe_image_link_status(VpeContext* ctx, int* timeouts);
 /* Composite R slabs' partial images for a pixel range in reference order (phase 1 slabs in
  * ascending z with OVER, then phase 2 slabs in ascending z with UNDER). parts_dev[2*r+0] = over,
  * parts_dev[2*r+1] = under of slab r (device pointers, numPixels*4 floats each). */

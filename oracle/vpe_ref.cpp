@@ -1166,6 +1166,11 @@ int vpe_sheet_link_connect(VpeContext* c, const void*, const void*, int) { retur
 int vpe_fill_sweep_linked(VpeContext* c) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
 int vpe_sheet_link_status(VpeContext* c, int*) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
 int vpe_march_partial_device(VpeContext* c, const VpeCamera*, float*, float*, int32_t*) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
+int vpe_image_link_create(VpeContext* c, int, int, int, int, void*, void**) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
+int vpe_image_link_connect(VpeContext* c, const void* const*, int) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
+int vpe_march_linked(VpeContext* c, const VpeCamera*, int32_t*) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
+int vpe_composite_linked(VpeContext* c, float*) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
+int vpe_image_link_status(VpeContext* c, int*) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
 int vpe_composite_device(VpeContext* c, const float* const*, int, int, float*) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
 
 // Oracle-only: host-side light sheet access for the slab hand-off tests.

@@ -177,6 +177,43 @@ def test_linked_sweep_other_brick_sizes_and_three_slabs(n_vox, grid, ranks_z):
     assert cov == one.stats()["numMetavoxelsCovered"] > 0
 
 
+def test_image_link_two_contexts_on_one_gpu():
+    """vpe_march_linked / vpe_composite_linked: the march kernel stores the partial images into the compositing
+    context's receive buffer and raises a flag; compositing from there equals compositing the partial images
+    (bit for bit: same kernel arithmetic), two frames in a row (both buffer parities)."""
+    import torch
+    sc = _scene()
+    cam = sc["camera"]
+    h, w = cam["height"], cam["width"]
+    per = -(-h // 2)
+    ranks = [slabs.CudaSlabEngine(sc, r, 2, 0) for r in range(2)]
+    for e in ranks:
+        e.fill_prepare(sc["particles"], sc["emitter"])
+    # fill through the two-phase path with a device copy of the sheet (as in test_two_slab_contexts_on_one_gpu)
+    for e in ranks:
+        e.fill_density()
+    ranks[0].fill_sweep_region(0, ranks[0].grid[0], 0, ranks[0].grid[1])
+    ranks[1].sheet_tensor().copy_(ranks[0].sheet_tensor())
+    ranks[1].fill_sweep_region(0, ranks[1].grid[0], 0, ranks[1].grid[1])
+    parts = []
+    for e in ranks:
+        over, under = e.march_partial(cam, per * 2)
+        parts += [over.clone(), under.clone()]
+    want = ranks[0].composite(parts, per * 2 * w).reshape(per * 2, w, 4).cpu().numpy()
+    ptrs = [e.eng.image_link_create(2, r, w, h)[1] for r, e in enumerate(ranks)]
+    for r, e in enumerate(ranks):
+        e.eng.image_link_connect([None if q == r else ptrs[q] for q in range(2)])
+    for frame in range(3):
+        for e in ranks:
+            e.march_linked(cam)
+        bands = [e.composite_linked(per, w).cpu().numpy() for e in ranks]
+        torch.cuda.synchronize()
+        assert all(e.eng.image_link_timeouts() == 0 for e in ranks)
+        got = np.concatenate(bands, axis=0)
+        assert np.array_equal(got, want), frame
+    assert float(want[..., 3].max()) > 0.3
+
+
 def test_linked_sweep_reports_a_missing_peer(monkeypatch):
     """A downstream rank whose upstream never arrives gives up after the spin limit and says so; it does
     not hang the GPU."""
@@ -216,12 +253,12 @@ def _nccl_worker(rank, world, port, out_dir):
         # the same over the sheet link (peer memory, CUDA IPC between the two processes), twice
         eng2 = slabs.CudaSlabEngine(sc, rank, world, rank)
         r2 = slabs.SlabRenderer(eng2, dist)
-        assert r2.linked
+        assert r2.linked and r2._image_link(sc["camera"]["width"], sc["camera"]["height"])
         for _ in range(2):
             r2.fill(sc["particles"], sc["emitter"])
         img2, total2 = r2.march(sc["camera"])
         torch.cuda.synchronize()
-        assert eng2.eng.sheet_link_timeouts() == 0
+        assert eng2.eng.sheet_link_timeouts() == 0 and eng2.eng.image_link_timeouts() == 0
         assert np.array_equal(eng2.eng.read_light_sheet(), sheet_nccl)
         if rank == 0:
             assert total2 == total and np.array_equal(img2.cpu().numpy(), img.cpu().numpy())

@@ -8,4 +8,5 @@ import json,sys
 d=json.loads(sys.stdin.read())
 print('$name N=$N ms/step=%.3f fill=%.3f march=%.3f (kernel %.3f) e2e_frame=%.3f' % (d['ms_per_step'], d['fill']['ms'], d['march']['ms'], d['march']['kernel_ms'], d['e2e']['frame_ms']))" || tail -5 gpurun_out/multi_${name}_$N.err; }
 run linked VPE_X=1
-run nccl VPE_SLAB_NCCL_SWEEP=1
+run ncclimage VPE_SLAB_NCCL_IMAGE=1
+[ -n "$WITH_NCCL" ] && run nccl VPE_SLAB_NCCL_SWEEP=1

@@ -100,6 +100,11 @@ PROTOTYPES = {
     "vpe_fill_sweep_linked": (C.c_int, [_P]),
     "vpe_sheet_link_status": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "vpe_march_partial_device": (C.c_int, [_P, C.POINTER(VpeCamera), _P, _P, _P]),
+    "vpe_image_link_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.POINTER(_P)]),
+    "vpe_image_link_connect": (C.c_int, [_P, C.POINTER(_P), C.c_int]),
+    "vpe_march_linked": (C.c_int, [_P, C.POINTER(VpeCamera), _P]),
+    "vpe_composite_linked": (C.c_int, [_P, _P]),
+    "vpe_image_link_status": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "vpe_composite_device": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_int, _P]),
     "vpe_march_footprint": (C.c_int, [_P, C.POINTER(VpeCamera), C.POINTER(C.c_int64)]),
     "vpe_read_brick": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),

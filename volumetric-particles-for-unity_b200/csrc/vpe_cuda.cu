@@ -91,6 +91,16 @@ struct VpeContext {
     bool linkUpIpc = false, linkDownIpc = false;
     int linkBlocks = 0;
     unsigned linkEpoch = 0;
+    // image link (multi-GPU march): receive buffer [2 parities][over|under][slab][row][col] float4 + flags, and
+    // every rank's buffer mapped into this process
+    void* imgOwn = nullptr;
+    void* imgPeers[64] = {};
+    bool imgPeerIpc[64] = {};
+    DevBuf<float4*> dImgPeers;
+    int imgWorld = 0, imgRank = 0, imgW = 0, imgH = 0, imgPer = 0;
+    size_t imgFlagsOff = 0, imgTimeoutOff = 0, imgBytes = 0;
+    unsigned imgEpoch = 0;
+    bool imgConnected = false;
     // host-path march: bands on two auxiliary streams, each copied home as soon as it is done
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // two compute streams + one copy stream
     cudaEvent_t evFork = nullptr, evJoin[3] = {nullptr, nullptr, nullptr};
@@ -368,7 +378,7 @@ struct HostImage {
 };
 
 int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nPixels, float4* rgbaDev, float4* underDev,
-               int* samplesDev, bool partial, unsigned* footprint = nullptr, HostImage* host = nullptr) {
+               int* samplesDev, bool partial, unsigned* footprint = nullptr, HostImage* host = nullptr, bool linked = false) {
     GridParams& g = c->g;
     const VpeConfig& k = c->cfg;
     if (cam->width < 1 || cam->height < 1) return fail(c, VPE_E_INVALID_ARG, "bad image size");
@@ -456,6 +466,13 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     a.mvCam = c->dMvCam.p; a.rankAsc = c->dRank.p; a.bricks = c->dBricks.p; a.pixels = pixelsDev;
     a.rgba = rgbaDev; a.under = underDev; a.samples = samplesDev; a.totalSamples = c->dTotalSamples.p;
     a.footprint = footprint;
+    a.peerRecv = nullptr;
+    a.linkWorld = a.linkRank = a.linkPer = a.linkParity = a.linkW = 0;
+    if (linked) {
+        a.peerRecv = c->dImgPeers.p;
+        a.linkWorld = c->imgWorld; a.linkRank = c->imgRank; a.linkPer = c->imgPer; a.linkW = c->imgW;
+        a.linkParity = (int)(c->imgEpoch & 1u);
+    }
     a.sceneDepth = c->sceneDepthSet ? c->dSceneDepth.p : nullptr;
     a.orderOf = nullptr;
     if (c->debugMode == 1) {
@@ -667,6 +684,10 @@ int vpe_destroy(VpeContext* c) {
     for (int i = 0; i < 32; i++)
         if (c->evBand[i]) cudaEventDestroy(c->evBand[i]);
     if (c->evFork) cudaEventDestroy(c->evFork);
+    for (int q = 0; q < 64; q++)
+        if (c->imgPeers[q] && c->imgPeerIpc[q]) cudaIpcCloseMemHandle(c->imgPeers[q]);
+    if (c->imgOwn) cudaFree(c->imgOwn);
+    c->dImgPeers.release();
     if (c->linkUp && c->linkUpIpc) cudaIpcCloseMemHandle(c->linkUp);
     if (c->linkDown && c->linkDownIpc) cudaIpcCloseMemHandle(c->linkDown);
     if (c->linkOwn) cudaFree(c->linkOwn);
@@ -986,6 +1007,105 @@ int vpe_march_partial_device(VpeContext* c, const VpeCamera* cam, float* over_de
     if (rc) return rc;
     cudaSetDevice(c->device);
     return march_impl(c, cam, nullptr, 0, reinterpret_cast<float4*>(over_dev), reinterpret_cast<float4*>(under_dev), samples_dev, true);
+}
+
+// ---- image link: the slab partial images go straight into the compositing ranks' memory ----
+int vpe_image_link_create(VpeContext* c, int world, int rank, int width, int height, void* ipcHandle64, void** devPtr) {
+    if (!c || world < 1 || world > 64 || rank < 0 || rank >= world || width < 1 || height < 1) return fail(c, VPE_E_INVALID_ARG, "bad image link geometry");
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->imgOwn && (c->imgWorld != world || c->imgRank != rank || c->imgW != width || c->imgH != height)) {
+        for (int q = 0; q < 64; q++) {
+            if (c->imgPeers[q] && c->imgPeerIpc[q]) cudaIpcCloseMemHandle(c->imgPeers[q]);
+            c->imgPeers[q] = nullptr; c->imgPeerIpc[q] = false;
+        }
+        cudaFree(c->imgOwn);
+        c->imgOwn = nullptr;
+        c->imgConnected = false;
+    }
+    if (!c->imgOwn) {
+        c->imgWorld = world; c->imgRank = rank; c->imgW = width; c->imgH = height;
+        c->imgPer = (height + world - 1) / world;
+        const size_t recv = (size_t)2 * 2 * world * c->imgPer * width * sizeof(float4);
+        c->imgFlagsOff = (recv + 255) / 256 * 256;
+        c->imgTimeoutOff = c->imgFlagsOff + (size_t)2 * world * sizeof(unsigned);
+        c->imgBytes = c->imgTimeoutOff + 256;
+        CUDA_TRY(c, cudaMalloc(&c->imgOwn, c->imgBytes));
+        CUDA_TRY(c, cudaMemset(c->imgOwn, 0, c->imgBytes));
+        c->imgEpoch = 0;
+    }
+    if (ipcHandle64) {
+        cudaIpcMemHandle_t h;
+        CUDA_TRY(c, cudaIpcGetMemHandle(&h, c->imgOwn));
+        memcpy(ipcHandle64, &h, sizeof(h));
+    }
+    if (devPtr) *devPtr = c->imgOwn;
+    return VPE_OK;
+}
+
+int vpe_image_link_connect(VpeContext* c, const void* const* peers, int handlesAreIpc) {
+    if (!c || !peers) return VPE_E_INVALID_ARG;
+    if (!c->imgOwn) return fail(c, VPE_E_NOT_READY, "vpe_image_link_create has not been called");
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    std::vector<float4*> ptrs(c->imgWorld);
+    for (int q = 0; q < c->imgWorld; q++) {
+        if (c->imgPeers[q] && c->imgPeerIpc[q]) cudaIpcCloseMemHandle(c->imgPeers[q]);
+        c->imgPeers[q] = nullptr; c->imgPeerIpc[q] = false;
+        if (q == c->imgRank) { ptrs[q] = static_cast<float4*>(c->imgOwn); continue; }
+        if (!peers[q]) return fail(c, VPE_E_INVALID_ARG, "image link: a peer is missing");
+        int rc = link_map(c, peers[q], handlesAreIpc, c->imgPeers[q], c->imgPeerIpc[q]);
+        if (rc) return rc;
+        ptrs[q] = static_cast<float4*>(c->imgPeers[q]);
+    }
+    CUDA_TRY(c, c->dImgPeers.ensure(c->imgWorld));
+    CUDA_TRY(c, cudaMemcpy(c->dImgPeers.p, ptrs.data(), sizeof(float4*) * c->imgWorld, cudaMemcpyHostToDevice));
+    c->imgConnected = true;
+    return VPE_OK;
+}
+
+int vpe_march_linked(VpeContext* c, const VpeCamera* cam, int32_t* samples_dev) {
+    if (!c || !cam) return fail(c, VPE_E_INVALID_ARG, "null argument");
+    int rc = check_ready_for_march(c);
+    if (rc) return rc;
+    if (!c->imgConnected) return fail(c, VPE_E_NOT_READY, "vpe_image_link_connect has not been called");
+    if (cam->width != c->imgW || cam->height != c->imgH) return fail(c, VPE_E_INVALID_ARG, "camera image size differs from the image link's");
+    cudaSetDevice(c->device);
+    c->imgEpoch++;
+    // the kernel stores into the receive buffers; rgba/under are placeholders that are never written
+    rc = march_impl(c, cam, nullptr, 0, static_cast<float4*>(c->imgOwn), static_cast<float4*>(c->imgOwn), samples_dev, true, nullptr, nullptr, true);
+    if (rc) return rc;
+    k_image_signal<<<1, 64, 0, c->stream>>>(c->dImgPeers.p, c->imgFlagsOff, c->imgWorld, c->imgRank, (int)(c->imgEpoch & 1u), c->imgEpoch);
+    CUDA_TRY(c, cudaGetLastError());
+    c->stats.marchLaunches++;
+    return VPE_OK;
+}
+
+int vpe_composite_linked(VpeContext* c, float* band_rgba_dev) {
+    if (!c || !band_rgba_dev) return fail(c, VPE_E_INVALID_ARG, "null argument");
+    if (!c->imgConnected || c->imgEpoch == 0) return fail(c, VPE_E_NOT_READY, "vpe_march_linked has not been called");
+    cudaSetDevice(c->device);
+    const int np = c->imgPer * c->imgW;
+    const char* ms = getenv("VPE_LINK_SPIN_MS");
+    const long long spin = (long long)(ms ? atof(ms) : 2000.0) * 2000000ll;
+    char* own = static_cast<char*>(c->imgOwn);
+    k_composite_linked<<<div_up(np, 256), 256, 0, c->stream>>>(reinterpret_cast<const float4*>(own), reinterpret_cast<const unsigned*>(own + c->imgFlagsOff),
+                                                             c->imgWorld, c->imgPer, c->imgW, (int)(c->imgEpoch & 1u), c->imgEpoch, spin,
+                                                             reinterpret_cast<unsigned*>(own + c->imgTimeoutOff), reinterpret_cast<float4*>(band_rgba_dev));
+    CUDA_TRY(c, cudaGetLastError());
+    return VPE_OK;
+}
+
+int vpe_image_link_status(VpeContext* c, int* timeouts) {
+    if (!c || !timeouts) return VPE_E_INVALID_ARG;
+    *timeouts = 0;
+    if (!c->imgOwn) return VPE_OK;
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    unsigned t = 0;
+    CUDA_TRY(c, cudaMemcpy(&t, static_cast<char*>(c->imgOwn) + c->imgTimeoutOff, sizeof(t), cudaMemcpyDeviceToHost));
+    *timeouts = (int)t;
+    return VPE_OK;
 }
 
 int vpe_composite_device(VpeContext* c, const float* const* parts_dev, int numSlabs, int numPixels, float* rgba_dev) {

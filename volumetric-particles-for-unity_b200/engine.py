@@ -236,6 +236,41 @@ class Engine:
         self._check(self.lib.vpe_sheet_link_status(self._ctx, C.byref(n)))
         return n.value
 
+    # -- image link: the slab partials go straight into the compositing ranks' memory (CUDA library only) ------
+    def image_link_create(self, world, rank, width, height):
+        h = (C.c_ubyte * 64)()
+        p = C.c_void_p()
+        self._check(self.lib.vpe_image_link_create(self._ctx, int(world), int(rank), int(width), int(height), h, C.byref(p)))
+        return bytes(h), p.value
+
+    def image_link_connect(self, peers):
+        """peers[q]: rank q's 64-byte IPC handle (bytes) or device pointer (int); the own entry may be None."""
+        kinds = {type(v) for v in peers if v is not None}
+        if len(kinds) != 1:
+            raise ValueError("peers must all be IPC handles or all device pointers")
+        ipc = bytes in kinds
+        keep, arr = [], (C.c_void_p * len(peers))()
+        for q, v in enumerate(peers):
+            if v is None:
+                arr[q] = None
+                continue
+            buf = C.create_string_buffer(v, 64) if ipc else C.pointer(C.c_void_p(int(v)))
+            keep.append(buf)
+            arr[q] = C.cast(buf, C.c_void_p)
+        self._check(self.lib.vpe_image_link_connect(self._ctx, arr, 1 if ipc else 0))
+
+    def march_linked(self, camera, samples_ptr=None):
+        c = _camera(camera)
+        self._check(self.lib.vpe_march_linked(self._ctx, C.byref(c), C.c_void_p(int(samples_ptr)) if samples_ptr else None))
+
+    def composite_linked(self, band_ptr):
+        self._check(self.lib.vpe_composite_linked(self._ctx, C.c_void_p(int(band_ptr))))
+
+    def image_link_timeouts(self):
+        n = C.c_int(0)
+        self._check(self.lib.vpe_image_link_status(self._ctx, C.byref(n)))
+        return n.value
+
     def march(self, camera, want_samples=True, out=None, samples_out=None):
         c = _camera(camera)
         rgba = out if out is not None else np.empty((c.height, c.width, 4), dtype=np.float32)

@@ -122,6 +122,7 @@ class SlabRenderer:
         self.bands = row_bands(gy, fill_bands if fill_bands is not None else default_fill_bands(engine.grid, engine.N, self.world))
         # sheet link: engines that can hand the sheet over through peer memory (CUDA, one node) do so;
         # fill_bands given explicitly (or VPE_SLAB_NCCL_SWEEP=1) keeps the NCCL send/recv band pipeline
+        self._image_links = {}
         self.profile = False          # record device times of the density pass and the march kernel (rebalance)
         self._times = None
         self.linked = False
@@ -157,6 +158,15 @@ class SlabRenderer:
             if self.rank < self.world - 1:
                 e.sheet_read(y0, y1)
                 d.send(rows, dst=self.rank + 1)
+
+    def _image_link(self, w, h):
+        """Set up (once per image size) the peer-memory exchange of the partial images; False = use NCCL."""
+        if not self.linked or not hasattr(self.e, "image_link_neighbours") or os.environ.get("VPE_SLAB_NCCL_IMAGE"):
+            return False
+        key = (w, h)
+        if key not in self._image_links:
+            self._image_links[key] = bool(self.e.image_link_neighbours(self.dist, self.rank, self.world, w, h))
+        return self._image_links[key]
 
     # -- load balance -----------------------------------------------------------------------------
     def set_slab(self, z0, z1):
@@ -198,20 +208,27 @@ class SlabRenderer:
         e, d = self.e, self.dist
         h, w = int(camera["height"]), int(camera["width"])
         per = -(-h // self.world)                    # image rows per owner; the image is padded to R * per rows
-        over, under = e.march_partial(camera, per * self.world)   # 2 x (R*per, W, 4), premultiplied; rows >= H stay 0
-        samples = e.last_ray_samples() if count_samples else None
-        if self.world == 1:
-            out = e.composite([over, under], h * w).reshape(h, w, 4)
-            return out, samples
-        # rows [q*per, (q+1)*per) of both partials go to rank q: the buffers are already laid out by owner
-        recv_over = e.buffer("recv_over", (self.world, per, w, 4))    # [slab][row][col][rgba]
-        recv_under = e.buffer("recv_under", (self.world, per, w, 4))
-        d.all_to_all_single(recv_over.view(-1), over.view(-1))
-        d.all_to_all_single(recv_under.view(-1), under.view(-1))
-        parts = []
-        for s in range(self.world):                  # ascending slab order = ascending z
-            parts += [recv_over[s], recv_under[s]]
-        band = e.composite(parts, per * w).reshape(per, w, 4)
+        if self.world > 1 and self._image_link(w, h):
+            # the march kernel stores every pixel's two partials straight into the receive buffer of the rank that
+            # composites its row (peer memory) and raises a flag; the composite kernel waits for all ranks' flags
+            e.march_linked(camera)
+            samples = e.last_ray_samples() if count_samples else None
+            band = e.composite_linked(per, w)
+        else:
+            over, under = e.march_partial(camera, per * self.world)   # 2 x (R*per, W, 4), premultiplied; rows >= H stay 0
+            samples = e.last_ray_samples() if count_samples else None
+            if self.world == 1:
+                out = e.composite([over, under], h * w).reshape(h, w, 4)
+                return out, samples
+            # rows [q*per, (q+1)*per) of both partials go to rank q: the buffers are already laid out by owner
+            recv_over = e.buffer("recv_over", (self.world, per, w, 4))    # [slab][row][col][rgba]
+            recv_under = e.buffer("recv_under", (self.world, per, w, 4))
+            d.all_to_all_single(recv_over.view(-1), over.view(-1))
+            d.all_to_all_single(recv_under.view(-1), under.view(-1))
+            parts = []
+            for s in range(self.world):                  # ascending slab order = ascending z
+                parts += [recv_over[s], recv_under[s]]
+            band = e.composite(parts, per * w).reshape(per, w, 4)
         total = e.all_reduce_sum(d, samples) if count_samples else None
         if not gather:
             r0, r1 = image_band(h, self.world, self.rank)
@@ -300,6 +317,28 @@ class CudaSlabEngine:
 
     def fill_sweep_linked(self):
         self.eng.fill_sweep_linked()
+
+    def image_link_neighbours(self, dist, rank, world, w, h):
+        """Exchange the IPC handles of the image receive buffers and map every rank's buffer (same node only)."""
+        handle, _ = self.eng.image_link_create(world, rank, w, h)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, handle)
+        ok = True
+        try:
+            self.eng.image_link_connect([None if q == rank else everyone[q] for q in range(world)])
+        except Exception:
+            ok = False
+        results = [None] * world
+        dist.all_gather_object(results, ok)
+        return all(results)
+
+    def march_linked(self, camera):
+        self.eng.march_linked(camera)
+
+    def composite_linked(self, per, w):
+        out = self.buffer("band", (per, w, 4))
+        self.eng.composite_linked(out.data_ptr())
+        return out
 
     def set_slab(self, z0, z1):
         self.eng.set_config(slabZBegin=int(z0), slabZEnd=int(z1))
@@ -474,9 +513,11 @@ def bench_multi_gpu(args, metric, measured_peak_hbm, ClockSampler):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %d^3 grid x %d^3 voxels, %d particles, %dx%d, %d steps/metavoxel" % (
             cfg_name, eng.grid[0], N, n, W, H, sc["rayMarchSteps"]),  # same string as bench.workload_name
-            "parallelism": "light-axis slabs x%d (fill: %s; march: slab-local + all-to-all ordered compositing)" % (
+            "parallelism": "light-axis slabs x%d (fill: %s; march: slab-local, %s, ordered compositing by screen band)" % (
                 world, "sweep kernel hands the sheet to the next rank over NVLink peer memory, one launch" if r.linked
-                else "sheet rows over NCCL send/recv in %d bands" % len(r.bands)),
+                else "sheet rows over NCCL send/recv in %d bands" % len(r.bands),
+                "partials stored into the compositing rank's memory by the march kernel (peer memory + flags)"
+                if r._image_links.get((W, H)) else "NCCL all-to-all of the partial images"),
             "slabs": [list(x) for x in slab_list],
             "cache": "inputs larger than L2 (brick pools %.2f GB in total); no flush between iterations" % (pool / 1e9),
             "covered_metavoxels": int(covered), "particle_metavoxel_pairs": int(pairs)},
