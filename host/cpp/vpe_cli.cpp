@@ -1,6 +1,6 @@
 // vpe_cli — headless driver of the C++ host mirror: renders `frames` frames of a particle file through
 // MetavoxelEngine::VolumetricParticleRenderer and writes the last frame's RGBA (raw float32) + a summary.
-//   vpe_cli <lib.so> <cubemap_r8.bin> <particles.f32 (n x 7)> <grid> <voxels> <mvScale> <width> <height> <camZ> <frames> <out.rgba>
+//   vpe_cli <lib.so> <cubemap_r8.bin> <particles.f32 (n x 7)> <grid> <voxels> <mvScale> <width> <height> <camZ> <frames> <out.rgba> [occluders.f32 (n x 9)]
 // Used by tests/test_host_cpp.py with libvpe_cuda.so (GPU) and, as a checker of the host logic only,
 // with the oracle library (CPU).
 #include <cstdio>
@@ -25,7 +25,9 @@ static std::vector<unsigned char> read_file(const char* path) {
 }
 
 int main(int argc, char** argv) {
-    if (argc != 12) { fprintf(stderr, "usage: see the header of vpe_cli.cpp\n"); return 2; }
+    // optional 12th argument: a file of occluder triangles (n x 9 float32, world space). The rest of the reference's
+    // frame is then run as well (VPR.cs:184,204,210): light depth map, 8-bit particlesRT, blend onto a blue scene.
+    if (argc != 12 && argc != 13) { fprintf(stderr, "usage: see the header of vpe_cli.cpp\n"); return 2; }
     VpeApi api;
     std::string why;
     if (!api.load(argv[1], &why)) { fprintf(stderr, "cannot load %s: %s\n", argv[1], why.c_str()); return 3; }
@@ -48,6 +50,15 @@ int main(int argc, char** argv) {
     const VpeParticle* parts = reinterpret_cast<const VpeParticle*>(pbytes.data());
     const int n = (int)(pbytes.size() / sizeof(VpeParticle));
     int fills = 0;
+    if (argc == 13) {
+        std::vector<unsigned char> tbytes = read_file(argv[12]);
+        if (tbytes.size() % (9 * sizeof(float))) { fprintf(stderr, "bad triangle file\n"); return 4; }
+        rc = r.RenderLightDepthMap(reinterpret_cast<const float*>(tbytes.data()), (int)(tbytes.size() / (9 * sizeof(float))));
+        if (rc) { fprintf(stderr, "RenderLightDepthMap: %d %s\n", rc, r.lastError().c_str()); return 8; }
+        VpeMarchOptions opt{};
+        opt.targetFormat = 1;
+        if ((rc = r.SetMarchOptions(opt))) { fprintf(stderr, "SetMarchOptions: %d %s\n", rc, r.lastError().c_str()); return 8; }
+    }
     for (int f = 0; f < frames; f++) {
         int before = r.numParticlesEmitted;
         r.numParticlesEmitted = -1;
@@ -57,6 +68,12 @@ int main(int argc, char** argv) {
     }
     VpeStats st;
     r.GetStats(&st);
+    if (argc == 13) {  // mainSceneRT: opaque blue; the particles are blended onto it, 8-bit like the reference's targets
+        std::vector<float> scene((size_t)width * height * 4);
+        for (size_t i = 0; i < scene.size(); i += 4) { scene[i] = 0.0f; scene[i + 1] = 0.0f; scene[i + 2] = 0.5f; scene[i + 3] = 1.0f; }
+        if ((rc = r.CompositeParticles(rgba.data(), scene.data(), width * height, 1))) { fprintf(stderr, "CompositeParticles: %d\n", rc); return 8; }
+        rgba = scene;
+    }
     FILE* o = fopen(argv[11], "wb");
     if (!o || fwrite(rgba.data(), sizeof(float), rgba.size(), o) != rgba.size()) { fprintf(stderr, "cannot write %s\n", argv[11]); return 7; }
     fclose(o);

@@ -72,12 +72,17 @@ def build_cli(tmp_path):
     return exe
 
 
-def run_cli(exe, lib_path, tmp_path, frames):
+def run_cli(exe, lib_path, tmp_path, frames, occluders=None):
     sc = scenes.make_scene("cfg1", image=(48, 48))
     pfile, out = str(tmp_path / "particles.f32"), str(tmp_path / "out.rgba")
     sc["particles"].astype(np.float32).tofile(pfile)
     cube = os.path.join(scenes.ASSET_DIR, "displacement_r8.bin")
-    res = subprocess.run([exe, lib_path, cube, pfile, "8", "8", "1.0", "48", "48", str(sc["camera"]["position"][2]), str(frames), out],
+    extra = []
+    if occluders is not None:
+        tfile = str(tmp_path / "occluders.f32")
+        np.ascontiguousarray(occluders, dtype=np.float32).tofile(tfile)
+        extra = [tfile]
+    res = subprocess.run([exe, lib_path, cube, pfile, "8", "8", "1.0", "48", "48", str(sc["camera"]["position"][2]), str(frames), out] + extra,
                          check=True, capture_output=True, text=True)
     summary = dict(kv.split("=") for kv in res.stdout.split())
     return np.fromfile(out, dtype=np.float32).reshape(48, 48, 4), summary
@@ -97,6 +102,42 @@ def test_cpp_mirror_over_the_oracle(tmp_path):
     want = r.OnPostRender(sc["particles"], sc["camera"])
     assert np.array_equal(img, want)
     assert int(summary["covered"]) == 218 and int(summary["pairs"]) == 457
+
+
+def _whole_frame_through_python(lib, sc):
+    import frame_scenes
+    r = make_renderer(lib, sc)
+    r.particlesRT_8bit = True
+    scene_rt = np.zeros((48, 48, 4), dtype=np.float32)
+    scene_rt[..., 2], scene_rt[..., 3] = 0.5, 1.0
+    return r.OnPostRender(sc["particles"], sc["camera"], occluders=frame_scenes.occluders(sc), mainSceneRT=scene_rt)
+
+
+def test_cpp_mirror_whole_frame_over_the_oracle(tmp_path):
+    """The C++ mirror's RenderLightDepthMap / SetMarchOptions / CompositeParticles (VPR.cs:184,210,228) against the
+    Python mirror, both over the oracle library."""
+    import frame_scenes
+    from oracle_lib import load_oracle, ORACLE_LIB
+    sc = scenes.make_scene("cfg1", image=(48, 48))
+    img, summary = run_cli(build_cli(tmp_path), ORACLE_LIB, tmp_path, frames=1, occluders=frame_scenes.occluders(sc))
+    want = _whole_frame_through_python(load_oracle(), sc)
+    assert np.array_equal(img, want)
+    assert np.array_equal(np.round(img * 255), img * 255) and (img[..., 3] >= 1.0).all()   # 8-bit, opaque scene below
+    assert img[..., 0].max() > 0.05 and abs(float(np.median(img[..., 2])) - 128.0 / 255) < 0.05
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_whole_frame_on_cuda(tmp_path):
+    import frame_scenes
+    sc = scenes.make_scene("cfg1", image=(48, 48))
+    img, summary = run_cli(build_cli(tmp_path), vpe_b200.CUDA_LIB_PATH, tmp_path, frames=1, occluders=frame_scenes.occluders(sc))
+    assert summary["backend"] == "cuda"
+    want = _whole_frame_through_python(None, sc)
+    assert np.array_equal(img, want)
+    from oracle_lib import load_oracle
+    ref = _whole_frame_through_python(load_oracle(), sc)
+    diff = np.abs(img - ref)
+    assert diff.max() <= 1.0 / 255 + 1e-6 and (diff > 1e-6).mean() < 5e-3
 
 
 @pytest.mark.gpu

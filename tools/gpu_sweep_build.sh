@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: gpu_sweep_build2.sh "<name>:<EXTRA flags>" ...   (rebuilds the library per variant on the GPU box; bench only)
+# usage: gpu_sweep_build.sh "<name>:<EXTRA flags>" ...   (rebuilds the library per variant on the GPU box; bench only)
 mkdir -p gpurun_out; rm -f gpurun_out/sweep_*.json
 for v in "$@"; do
   name=${v%%:*}; flags=${v#*:}
