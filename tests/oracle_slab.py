@@ -14,6 +14,7 @@ class OracleSlabEngine:
     def __init__(self, scene, rank, world):
         from vpe_b200 import scenes
         self.lib = load_oracle()
+        self.scene = scene
         self.slab = slabs.slab_range(scene["grid"][2], world, rank)
         self.eng = oracle_engine(scene, slab=self.slab)
         scenes.apply_scene(self.eng, scene)
@@ -81,3 +82,22 @@ class OracleSlabEngine:
         t = torch.tensor([value], dtype=torch.int64)
         dist.all_reduce(t)
         return int(t.item())
+
+    # -- load balancing (SlabRenderer.rebalance): the oracle's slab is fixed at create, so a moved slab is a new context;
+    # "times" are deterministic stand-ins (particle pairs of the slab for the density pass, ray samples for the march)
+    def set_slab(self, z0, z1):
+        from vpe_b200 import scenes
+        self.slab = (int(z0), int(z1))
+        self.eng = oracle_engine(self.scene, slab=self.slab)
+        scenes.apply_scene(self.eng, self.scene)
+
+    def record_event(self):
+        return None
+
+    def elapsed_ms(self, a, b):
+        return float(self.eng.stats()["numParticlePairs"]) * 1e-2
+
+    def stats(self):
+        st = self.eng.stats()
+        st["marchKernelMs"] = float(st["raySamples"]) * 1e-5
+        return st

@@ -49,6 +49,57 @@ def _free_port():
     return p
 
 
+def _rebalance_worker(rank, world, port, out_dir):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), here):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from oracle_slab import OracleSlabEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sc = _scene()
+        eng = OracleSlabEngine(sc, rank, world)
+        r = slabs.SlabRenderer(eng, dist, fill_bands=2)
+        r.profile = True
+        r.fill(sc["particles"], sc["emitter"])
+        r.march(sc["camera"], gather=False)
+        new_slabs = r.rebalance()
+        r.profile = False
+        assert tuple(eng.slab) == tuple(new_slabs[rank]) == (r.z0, r.z1)
+        r.fill(sc["particles"], sc["emitter"])
+        img, total = r.march(sc["camera"])
+        np.savez(os.path.join(out_dir, "rb%d.npz" % rank), slabs=np.asarray(new_slabs), total=np.int64(total),
+                 img=img.numpy() if img is not None else np.zeros(0, np.float32), sheet=eng.eng.read_light_sheet())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rebalanced_slabs_render_the_same_image(tmp_path):
+    """SlabRenderer.rebalance over gloo: every rank derives the same contiguous partition from the gathered costs,
+    moves its slab, and the frame rendered with the new slabs is the single-context frame."""
+    from oracle_lib import oracle_engine
+    world = 3
+    sc = _scene()
+    ref = oracle_engine(sc)
+    scenes.apply_scene(ref, sc)
+    ref.fill(sc["particles"], sc["emitter"])
+    img_ref, smp_ref = ref.march(sc["camera"])
+    mp.spawn(_rebalance_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    outs = [np.load(os.path.join(str(tmp_path), "rb%d.npz" % r)) for r in range(world)]
+    parts = [tuple(map(tuple, o["slabs"])) for o in outs]
+    assert parts[0] == parts[1] == parts[2]
+    cuts = parts[0]
+    assert cuts[0][0] == 0 and cuts[-1][1] == ref.grid[2] and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+    assert all(b > a for a, b in cuts)
+    assert all(int(o["total"]) == int(smp_ref.sum()) for o in outs)
+    assert np.array_equal(outs[-1]["sheet"], ref.read_light_sheet())
+    assert max_rel_err(outs[0]["img"], img_ref) <= 1e-5
+
+
 def _worker(rank, world, port, out_dir, bands):
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
