@@ -96,6 +96,38 @@ namespace MetavoxelEngine
             Graphics.Blit(particlesTex, mainSceneRT, matBlendParticles);
         }
 
+        // replaces `lightCamera.GetComponent<Camera>().RenderWithShader(generateLightDepthMapShader, ...)` (VPR.cs:184):
+        // the meshes of the Default layer (the light camera's cullingMask, VPR.cs:346) as world-space triangles,
+        // Unity winding as is (GenerateLightDepthMap.shader:6 culls front faces).
+        void LightDepthMapNative(MeshFilter[] occluders)
+        {
+            var tris = new System.Collections.Generic.List<float>();
+            foreach (MeshFilter mf in occluders)
+            {
+                Mesh m = mf.sharedMesh;
+                Vector3[] v = m.vertices;
+                int[] idx = m.triangles;
+                Matrix4x4 l2w = mf.transform.localToWorldMatrix;
+                for (int i = 0; i < idx.Length; i++)
+                {
+                    Vector3 w = l2w.MultiplyPoint3x4(v[idx[i]]);
+                    tris.Add(w.x); tris.Add(w.y); tris.Add(w.z);
+                }
+            }
+            if (Vpe.vpe_render_light_depth_map(vpe, tris.ToArray(), tris.Count / 9) != 0) Debug.LogError("[VPE] " + Vpe.LastError(vpe));
+        }
+
+        // the debug views of SetRaymarchPassConstants (VPR.cs:744-761) and the 8-bit particlesRT (VPR.cs:228);
+        // sceneDepth (eye-space depth of mainSceneRT, VPR.cs:204) is left out here: pass a pinned float[] if wanted
+        void MarchOptionsNative(bool eightBitTarget)
+        {
+            VpeMarchOptions o = new VpeMarchOptions();
+            o.targetFormat = eightBitTarget ? 1 : 0;
+            o.debugMode = bShowMetavoxelDrawOrder ? 1 : bShowRayMarchBlendFunc ? 2 : bShowRayMarchSamplesPerPixel ? 3 : 0;
+            o.sceneDepth = IntPtr.Zero;
+            Vpe.vpe_set_march_options(vpe, ref o);
+        }
+
         void OnDestroy() { if (vpe != IntPtr.Zero) Vpe.vpe_destroy(vpe); }
     }
 }
