@@ -66,6 +66,22 @@ def check_frame_structure(lib):
     return f0
 
 
+def test_metavoxel_wire_grid_over_the_oracle():
+    """DrawMetavoxelGrid (VPR.cs:962-1033): 12 edges per covered metavoxel, each of length mvScale, centred on mPos."""
+    from oracle_lib import load_oracle
+    sc = scenes.make_scene("cfg1", image=(32, 32))
+    r = make_renderer(load_oracle(), sc)
+    r.FillMetavoxels(sc["particles"])
+    lines = r.DrawMetavoxelGrid()
+    assert lines.shape == (r.numMetavoxelsCovered, 12, 2, 3) and r.numMetavoxelsCovered == 218
+    length = np.linalg.norm(lines[:, :, 1] - lines[:, :, 0], axis=-1)
+    assert np.allclose(length, sc["mvScale"], atol=1e-5)
+    centre = lines.reshape(lines.shape[0], 24, 3).mean(axis=1)
+    covered = [(x, y, z) for z in range(8) for y in range(8) for x in range(8) if r.engine.read_particle_list(x, y, z).shape[0]]
+    want = np.array([r.engine.read_metavoxel_position(*c) for c in covered])
+    assert np.allclose(centre, want, atol=1e-5)
+
+
 def build_cli(tmp_path):
     exe = str(tmp_path / "vpe_cli")
     subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "host", "cpp", "vpe_cli.cpp"), "-ldl"], check=True)

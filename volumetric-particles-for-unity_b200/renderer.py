@@ -98,6 +98,30 @@ class VolumetricParticleRenderer:
         rgba, samples = self._engine.march(camera, want_samples=show_samples)
         return (rgba, samples) if show_samples else rgba
 
+    def DrawMetavoxelGrid(self):
+        """VPR.cs:962-1033 (bShowMetavoxelGrid): the wire cube of every covered metavoxel as world-space line
+        segments, shape (covered, 12, 2, 3), in the reference's vertex order (left face, right face, the four
+        joining edges). Drawing them (GL.LINES over mainSceneRT) is left to the host application."""
+        e = self._engine
+        q = np.asarray(self.dirLight["rotation"], dtype=np.float64)
+        hw, hh, hd = [0.5 * float(v) for v in self.mvScale]
+        corner = {}
+        for name, v in (("BLB", (-hw, -hh, hd)), ("BLF", (-hw, -hh, -hd)), ("TLB", (-hw, hh, hd)), ("TLF", (-hw, hh, -hd)),
+                        ("BRB", (hw, -hh, hd)), ("BRF", (hw, -hh, -hd)), ("TRB", (hw, hh, hd)), ("TRF", (hw, hh, -hd))):
+            corner[name] = scenes.quat_rotate(q, np.asarray([v]))[0]           # lightOrientation * offset (VPR.cs:989-996)
+        edges = [("BLB", "BLF"), ("BLF", "TLF"), ("TLF", "TLB"), ("TLB", "BLB"),     # left   (VPR.cs:998-1006)
+                 ("BRB", "BRF"), ("BRF", "TRF"), ("TRF", "TRB"), ("TRB", "BRB"),     # right  (VPR.cs:1007-1015)
+                 ("TLB", "TRB"), ("TLF", "TRF"), ("BLB", "BRB"), ("BLF", "BRF")]     # joins  (VPR.cs:1016-1025)
+        out = []
+        for zz in range(self.numMetavoxelsZ):
+            for yy in range(self.numMetavoxelsY):
+                for xx in range(self.numMetavoxelsX):
+                    if e.read_particle_list(xx, yy, zz).shape[0] == 0:     # mParticlesCovered.Count != 0 (VPR.cs:970)
+                        continue
+                    pos = e.read_metavoxel_position(xx, yy, zz).astype(np.float64)
+                    out.append([[pos + corner[a], pos + corner[b]] for a, b in edges])
+        return np.asarray(out, dtype=np.float32).reshape(-1, 12, 2, 3)
+
     # -- GUI callback setters, VPR.cs:1040-1119 -------------------------------------------------
     def SetDisplacementScale(self, ds):
         self.fDisplacementScale = float(ds)
