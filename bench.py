@@ -221,6 +221,8 @@ def run_cuda(args):
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     scenes.apply_scene(eng, sc)
+    if args.march_kernel or args.no_skip:
+        eng.set_debug_options(march_kernel=args.march_kernel, no_skip=args.no_skip)
     cam = sc["camera"]
     W, H = cam["width"], cam["height"]
     n = sc["particles"].shape[0]
@@ -337,6 +339,8 @@ def main():
     ap.add_argument("--config", default=None, help="cfg1..cfg5 (default: cfg3 at N=1)")
     ap.add_argument("--early-out", type=float, default=0.0, help="marchEarlyOutTransmittance (0 = exact reference semantics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--march-kernel", type=int, default=0, help="VpeDebugOptions.marchKernel (experiments): 1 = general kernel, 2 = round 1's per-fragment loop")
+    ap.add_argument("--no-skip", action="store_true", help="experiments: sample every step (ignore the empty-space bitmap)")
     ap.add_argument("--no-rebalance", action="store_true", help="N>1: keep equal slabs (default: balance the slab boundaries during warm-up)")
     ap.add_argument("--fill-bands", type=int, default=0, help="N>1: row bands of the fill pipeline (default: one per metavoxel row)")
     args = ap.parse_args()

@@ -237,6 +237,22 @@ int vpe_image_link_status(VpeContext* ctx, int* timeouts);
 int vpe_composite_device(VpeContext* ctx, const float* const* parts_dev, int numSlabs,
                          int numPixels, float* rgba_dev);
 
+/* ---- debug / experiment switches (CUDA library; the oracle accepts and ignores them) ----
+ * All zero = production behaviour. Read by the calls that follow; a change of noGray / noRowPad changes the
+ * brick layout, so the volume must be filled again before the next march. */
+typedef struct VpeDebugOptions {
+    int32_t marchKernel;    /* 0 = production (k_march_flat); 1 = general kernel (the shader's unfused sequence, the one
+                               march options and border 0 use); 2 = round 1's per-fragment loop (k_march), for comparison */
+    int32_t noSkip;         /* 1 = sample every step: ignore the empty-space bitmap                                       */
+    int32_t noGray;         /* 1 = keep half4 (r,g,b,density) texels even when the ambient colour is grey                  */
+    int32_t noRowPad;       /* 1 = brick rows N texels apart (no 64-byte pad)                                             */
+    int32_t marchBands;     /* host-buffer march: 0 = default (6 bands, copies overlapped), 1 = one launch + one copy, n   */
+    int32_t marchTileLog2W; /* warp pixel tile: 0 = default (8x4), else 1 + log2(width): 1 = 1x32 ... 6 = 32x1             */
+    int32_t linkSpinMs;     /* sheet / image link: how long a kernel waits for a peer, 0 = default (2000)                  */
+    int32_t reserved[9];
+} VpeDebugOptions;
+int vpe_set_debug_options(VpeContext* ctx, const VpeDebugOptions* options);
+
 /* ---- measurement ----
  * Number of distinct volume texels in the union of all samples' 8-texel trilinear footprints for
  * this camera (the march's compulsory read set = 8 B x this + 16 B x pixels).

@@ -1036,6 +1036,9 @@ int vpe_read_light_depth_map(VpeContext* c, float* depth01) {
     return VPE_OK;
 }
 
+// debug switches select kernels / layouts of the CUDA library; the oracle has one path and ignores them
+int vpe_set_debug_options(VpeContext* c, const VpeDebugOptions* o) { return (c && o) ? VPE_OK : VPE_E_INVALID_ARG; }
+
 int vpe_set_march_options(VpeContext* c, const VpeMarchOptions* o) {
     if (!c || !o) return VPE_E_INVALID_ARG;
     if (o->targetFormat < 0 || o->targetFormat > 1 || o->debugMode < 0 || o->debugMode > 3) return fail(c, VPE_E_INVALID_ARG, "bad march option");

@@ -67,7 +67,7 @@ def test_full_size_against_oracle_sample(cfg, tile):
     assert float(rgba_r[:, 3].max()) > 0.5
 
 
-def test_cfg3_full_frame_properties(monkeypatch):
+def test_cfg3_full_frame_properties():
     sc = scenes.make_scene("cfg3")
     cam = sc["camera"]
     gpu = vpe_b200.engine_for_scene(None, sc)
@@ -86,12 +86,16 @@ def test_cfg3_full_frame_properties(monkeypatch):
     img2, smp2 = gpu.march(cam)
     assert np.array_equal(img1, img2) and np.array_equal(smp1, smp2)
     # the three sample loops agree on the whole 1080p frame
-    monkeypatch.setenv("VPE_MARCH_NO_SKIP", "1")
+    gpu.set_debug_options(no_skip=True)
     img_all, smp_all = gpu.march(cam)
-    monkeypatch.setenv("VPE_MARCH_LEGACY", "1")
+    gpu.set_debug_options(no_skip=True, march_kernel=1)       # the general kernel: the shader's unfused sequence
     img_leg, smp_leg = gpu.march(cam)
-    assert np.array_equal(smp_all, smp1) and np.array_equal(smp_leg, smp1)
+    gpu.set_debug_options(march_kernel=2)                     # round 1's per-fragment loop
+    img_frag, smp_frag = gpu.march(cam)
+    gpu.set_debug_options()
+    assert np.array_equal(smp_all, smp1) and np.array_equal(smp_leg, smp1) and np.array_equal(smp_frag, smp1)
     assert max_rel_err(img1, img_all) <= 1e-5
+    assert max_rel_err(img1, img_frag) <= 1e-5
     assert max_rel_err(img1, img_leg) <= RTOL
     # the compulsory read set is a property of the samples, not of the kernel variant
     assert gpu.march_footprint(cam) == 715954156

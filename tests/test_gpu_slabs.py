@@ -214,13 +214,13 @@ def test_image_link_two_contexts_on_one_gpu():
     assert float(want[..., 3].max()) > 0.3
 
 
-def test_linked_sweep_reports_a_missing_peer(monkeypatch):
+def test_linked_sweep_reports_a_missing_peer():
     """A downstream rank whose upstream never arrives gives up after the spin limit and says so; it does
     not hang the GPU."""
     import torch
-    monkeypatch.setenv("VPE_LINK_SPIN_MS", "20")
     sc = _scene()
     ranks = [slabs.CudaSlabEngine(sc, r, 2, 0) for r in range(2)]
+    ranks[1].eng.set_debug_options(link_spin_ms=20)
     ptrs = [e.eng.sheet_link_create()[1] for e in ranks]
     ranks[1].eng.sheet_link_connect(ptrs[0], None)
     ranks[1].fill_prepare(sc["particles"], sc["emitter"])

@@ -34,6 +34,20 @@ using namespace vpe;
         }                                                                                            \
     } while (0)
 
+// Entry points run on the context's device and leave the caller's current device as they found it.
+struct DeviceScope {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceScope(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) ok = cudaSetDevice(device) == cudaSuccess;
+        else prev = -1;
+    }
+    ~DeviceScope() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -76,8 +90,9 @@ struct VpeContext {
     DevBuf<float> dCube, dDepth, dSheet;
     DevBuf<float4> dCubeFp;          // bilinear footprints of the cubemap, [6][E+1][E+1]
     DevBuf<uint2> dBricks;
-    DevBuf<unsigned> dOcc;           // occupancy cells per brick (skip empty space in the march)
-    int occCells = 0;                // 0 = occupancy off (N > 128)
+    DevBuf<unsigned> dNz, dOcc;      // per brick [z][y] rows of occRowWords words, bit x: non-zero density / occupied sample base (k_occ_build)
+    int occRowWords = 0;             // ceil(N / 32)
+    VpeDebugOptions dbg;             // vpe_set_debug_options (all zero = production behaviour)
     DevBuf<float4> dMvCam;
     DevBuf<int> dRank, dPixels, dSamples;
     DevBuf<float4> dImage, dImage2;
@@ -144,7 +159,13 @@ int validate_config(const VpeConfig& c, std::string& why) {
     // fill clamps the border to [0,N-2] (VPR.cs:528), the march does not (VPR.cs:726)
     if (c.numBorderVoxels < 0 || c.numBorderVoxels > (c.numVoxelsInMetavoxel - 2) / 2) { why = "numBorderVoxels out of range"; return -1; }
     if (!(c.mvScale > 0.0f)) { why = "mvScale must be > 0"; return -1; }
-    if (c.rayMarchSteps < 1) { why = "rayMarchSteps must be >= 1"; return -1; }
+    if (c.rayMarchSteps < 1 || c.rayMarchSteps > 32768) { why = "rayMarchSteps must be in [1, 32768]"; return -1; }
+    // values that would divide by zero or poison every voxel with NaN later on
+    if (!(c.lightFar > c.lightNear) || !std::isfinite(c.lightFar) || !std::isfinite(c.lightNear)) { why = "lightFar must be > lightNear (finite)"; return -1; }
+    if (c.softParticleStepDistance < 0) { why = "softParticleStepDistance must be >= 0"; return -1; }
+    if (!std::isfinite(c.mvScale) || !std::isfinite(c.opacityFactor) || !std::isfinite(c.displacementScale) || !std::isfinite(c.lightCameraDistance) ||
+        !std::isfinite(c.ambientColor[0]) || !std::isfinite(c.ambientColor[1]) || !std::isfinite(c.ambientColor[2]) ||
+        !std::isfinite(c.marchEarlyOutTransmittance)) { why = "non-finite float in the configuration"; return -1; }
     if (c.slabZBegin < 0 || c.slabZEnd > c.numMetavoxelsZ || c.slabZBegin >= c.slabZEnd) { why = "bad slab range"; return -1; }
     return 0;
 }
@@ -208,10 +229,10 @@ void rebuild_grid_params(VpeContext* c) {
         const float cmax = std::max(fabsf(g.center.x), std::max(fabsf(g.center.y), fabsf(g.center.z)));
         g.worldReach = cmax + 0.5f * 1.7320508f * (maxG + 2.0f) * g.sb * 1.01f;
     }
-    g.rowStride = g.N + ((g.N % 16 == 0 && !getenv("VPE_NO_ROWPAD")) ? ROW_PAD : 0);
+    g.rowStride = g.N + ((g.N % 16 == 0 && !c->dbg.noRowPad) ? ROW_PAD : 0);
     // r == g == b in every texel iff the three ambient components are the same bits (Fill.shader:244)
     g.gray = (memcmp(&k.ambientColor[0], &k.ambientColor[1], sizeof(float)) == 0 &&
-              memcmp(&k.ambientColor[1], &k.ambientColor[2], sizeof(float)) == 0 && !getenv("VPE_NO_GRAY")) ? 1 : 0;
+              memcmp(&k.ambientColor[1], &k.ambientColor[2], sizeof(float)) == 0 && !c->dbg.noGray) ? 1 : 0;
 }
 
 int sync_stream(VpeContext* c) {
@@ -274,10 +295,14 @@ int fill_prepare_impl(VpeContext* c, const float* particlesDev, int n, const Vpe
             return fail(c, VPE_E_OUT_OF_MEMORY, "brick pool does not fit in device memory");
         }
     }
-    if (c->occCells) {
-        const size_t words = std::max<size_t>(1, (size_t)c->nCovered * c->occCells * c->occCells);
-        CUDA_TRY(c, c->dOcc.ensure(words + words / 16));
-        CUDA_TRY(c, cudaMemsetAsync(c->dOcc.p, 0, words * sizeof(unsigned), c->stream));
+    {
+        // empty-space bitmaps: every word of a covered brick is rewritten by each fill (k_fill_columns / k_occ_build)
+        const size_t words = std::max<size_t>(1, (size_t)c->nCovered * g.N * g.N * c->occRowWords);
+        if (words > c->dNz.cap) {
+            CUDA_TRY(c, c->dNz.ensure(words + words / 16));
+            CUDA_TRY(c, c->dOcc.ensure(words + words / 16));
+            CUDA_TRY(c, cudaMemsetAsync(c->dNz.p, 0, c->dNz.cap * sizeof(unsigned), c->stream));  // the pad bytes of short rows
+        }
     }
     // VPR.cs:498-499: clear the light propagation texture to 1
     const size_t sheetN = (size_t)g.NX * g.N * g.NY * g.N;
@@ -317,7 +342,7 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1, FillPhase ph
     a.covered = c->dCovered.p; a.sliceStart = c->dSliceStart.p; a.cellStart = c->dCellStart.p; a.pairs = c->dPairs.p;
     a.pfill = c->dPfill.p; a.cube = c->dCube.p; a.depth = c->depthSet ? c->dDepth.p : nullptr;
     a.sheet = c->dSheet.p; a.bricks = c->dBricks.p;
-    a.occ = c->occCells ? c->dOcc.p : nullptr; a.occCells = c->occCells;
+    a.nz = reinterpret_cast<unsigned char*>(c->dNz.p); a.nzRowBytes = c->occRowWords * 4;
     a.x0 = x0; a.x1 = x1; a.y0 = y0; a.y1 = y1;
     CUDA_TRY(c, cudaEventRecord(c->evFillK0, c->stream));
     if (phase != FILL_DENSITY) c->bricksGray = g.gray != 0;
@@ -346,14 +371,17 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1, FillPhase ph
                     link.downFlag = reinterpret_cast<unsigned*>(static_cast<char*>(c->linkDown) + l.flagOff);
                 }
                 link.epoch = ++c->linkEpoch;
-                const char* ms = getenv("VPE_LINK_SPIN_MS");
-                link.spinLimit = (long long)(ms ? atof(ms) : 2000.0) * 2000000ll;  // ~2 GHz ticks
+                link.spinLimit = (long long)(c->dbg.linkSpinMs > 0 ? c->dbg.linkSpinMs : 2000) * 2000000ll;  // ~2 GHz ticks
                 if (g.gray) k_sweep_columns<true, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
                 else k_sweep_columns<false, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
             } else if (g.gray) k_sweep_columns<true, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
             else k_sweep_columns<false, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
         }
         c->stats.fillLaunches++;
+        if ((phase == FILL_FUSED || phase == FILL_DENSITY) && c->nCovered > 0) {  // the densities are final: derive the march's bitmap
+            k_occ_build<<<dim3((x1 - x0) * (y1 - y0), g.z1 - g.z0), 256, 0, c->stream>>>(g, c->dBrickOf.p, c->dNz.p, c->dOcc.p, c->occRowWords, x0, x1, y0);
+            c->stats.fillLaunches++;
+        }
     }
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaEventRecord(c->evFill1, c->stream));
@@ -480,15 +508,12 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
         k_order_index<<<div_up(c->numCells, 128), 128, 0, c->stream>>>(g, m, c->dBrickOf.p, c->dRank.p, c->dSliceStart.p, c->dOrderOf.p);
         a.orderOf = c->dOrderOf.p;
     }
-    const bool skip = c->occCells > 0 && !getenv("VPE_MARCH_NO_SKIP");
-    a.occ = skip ? c->dOcc.p : nullptr; a.occCells = c->occCells;
+    const bool skip = !c->dbg.noSkip;
+    a.occ = skip ? c->dOcc.p : nullptr; a.occRowWords = c->occRowWords;
     // Warp pixel tile. Measured on cfg3 (profiles/): the compact 8x4 tile wins over strips that follow
     // the bricks' 128-byte rows, because lanes of a strip sit in different bricks and diverge.
     {
-        int lw = 3;
-        const char* ov = getenv("VPE_MARCH_TILE_LOG2W");
-        if (ov && ov[0] >= '0' && ov[0] <= '5' && !ov[1]) lw = ov[0] - '0';
-        m.tileLog2W = lw;
+        m.tileLog2W = (c->dbg.marchTileLog2W >= 1 && c->dbg.marchTileLog2W <= 6) ? c->dbg.marchTileLog2W - 1 : 3;
     }
     dim3 grid, block(128);
     int ctaRows = 1;  // image rows per row of CTAs
@@ -501,11 +526,10 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     }
     // bands (host path): only worth it for a large image going to pinned memory
     int numBands = 1;
-    if (host && host->rgba && !pixelsDev && !partial && !footprint && (int)grid.y >= 32 && m.numPixels >= (1 << 19) && !getenv("VPE_MARCH_NO_BANDS")) {
+    if (host && host->rgba && !pixelsDev && !partial && !footprint && (int)grid.y >= 32 && m.numPixels >= (1 << 19) && c->dbg.marchBands != 1) {
         cudaPointerAttributes at;
-        const char* nb = getenv("VPE_MARCH_BANDS");
         if (cudaPointerGetAttributes(&at, host->rgba) == cudaSuccess && at.type == cudaMemoryTypeHost)
-            numBands = nb ? std::min(std::max(atoi(nb), 1), 32) : 6;  // measured on cfg3: 4-8 bands 7.40-7.46 ms, 16 bands 8.7, one launch + one copy 7.86
+            numBands = c->dbg.marchBands > 1 ? std::min(c->dbg.marchBands, 32) : 6;  // measured on cfg3: 4-8 bands 7.40-7.46 ms, 16 bands 8.7, one launch + one copy 7.86
         else cudaGetLastError();
         if (numBands > 1 && host->samples) {
             if (!(cudaPointerGetAttributes(&at, host->samples) == cudaSuccess && at.type == cudaMemoryTypeHost)) { cudaGetLastError(); numBands = 1; }
@@ -529,11 +553,11 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
         cudaStream_t st = numBands > 1 ? c->aux[band & 1] : c->stream;
         const int by0 = (int)((long long)band * fullGrid.y / numBands), by1 = (int)((long long)(band + 1) * fullGrid.y / numBands);
         if (numBands > 1) { grid = dim3(fullGrid.x, by1 - by0); m.blockYBase = by0; }
-        const bool legacy = m.wrap || optionsActive || getenv("VPE_MARCH_LEGACY");
+        const bool legacy = m.wrap || optionsActive || c->dbg.marchKernel == 1;
         const bool gray = c->bricksGray;  // the layout the fill wrote (z-paired grey texels or half4)
-        // k_march_merged trades divergence (26.6 instead of 23 active lanes) for a longer loop with lanes in
-        // different bricks: 7.75 vs 7.2 ms on cfg3 (profiles/r01_final_summary.md). Opt-in.
-        const bool merged = getenv("VPE_MARCH_MERGED") != nullptr;
+        // k_march_flat (one sample loop per ray and slice) is the production kernel; round 1's per-fragment loop
+        // remains selectable for comparison (VpeDebugOptions.marchKernel = 2).
+        const bool flat = c->dbg.marchKernel != 2;
 #define VPE_LAUNCH_MARCH3(KERNEL, ...)                                                                  \
     do {                                                                                                \
         if (skip && gray) KERNEL<__VA_ARGS__, true, true, PAD_><<<grid, block, 0, st>>>(g, m, a); \
@@ -544,7 +568,7 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
 #define VPE_LAUNCH_MARCH2(NT, PAD)                           \
     do {                                                     \
         constexpr bool PAD_ = PAD;                           \
-        if (merged) VPE_LAUNCH_MARCH3(k_march_merged, NT);   \
+        if (flat) VPE_LAUNCH_MARCH3(k_march_flat, NT);       \
         else VPE_LAUNCH_MARCH3(k_march, NT, false);          \
     } while (0)
 #define VPE_LAUNCH_MARCH(NT)                     \
@@ -625,7 +649,8 @@ int vpe_create(const VpeConfig* cfg, int device, VpeContext** out) {
     if (validate_config(c2, why)) return VPE_E_INVALID_ARG;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return VPE_E_CUDA;  // no fallback
-    if (cudaSetDevice(device) != cudaSuccess) return VPE_E_CUDA;
+    DeviceScope deviceScope(device);
+    if (!deviceScope.ok) { cudaGetLastError(); return VPE_E_CUDA; }
     VpeContext* c = new VpeContext();
     c->cfg = c2;
     c->device = device;
@@ -633,7 +658,8 @@ int vpe_create(const VpeConfig* cfg, int device, VpeContext** out) {
     memset(&c->light, 0, sizeof(c->light));
     c->light.rotation[3] = 1.0f;
     c->numCells = c2.numMetavoxelsX * c2.numMetavoxelsY * c2.numMetavoxelsZ;
-    c->occCells = c2.numVoxelsInMetavoxel <= 128 ? ((c2.numVoxelsInMetavoxel - 1) >> 2) + 1 : 0;
+    c->occRowWords = (c2.numVoxelsInMetavoxel + 31) / 32;
+    memset(&c->dbg, 0, sizeof(c->dbg));
     rebuild_grid_params(c);
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     c->ownStream = ok;
@@ -668,12 +694,12 @@ int vpe_create(const VpeConfig* cfg, int device, VpeContext** out) {
 
 int vpe_destroy(VpeContext* c) {
     if (!c) return VPE_OK;
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->dParticles.release(); c->dPfill.release(); c->dPbin.release();
     c->dCellCount.release(); c->dCellStart.release(); c->dBrickOf.release(); c->dCovered.release();
     c->dSliceStart.release(); c->dPairs.release(); c->dTotals.release(); c->dBlockSums.release();
-    c->dCube.release(); c->dCubeFp.release(); c->dDepth.release(); c->dSheet.release(); c->dBricks.release(); c->dOcc.release(); c->dMvCam.release();
+    c->dCube.release(); c->dCubeFp.release(); c->dDepth.release(); c->dSheet.release(); c->dBricks.release(); c->dNz.release(); c->dOcc.release(); c->dMvCam.release();
     c->dRank.release(); c->dPixels.release(); c->dSamples.release(); c->dImage.release(); c->dImage2.release();
     c->dTotalSamples.release(); c->dParts.release();
     c->dSceneDepth.release(); c->dOrderOf.release(); c->dTris.release(); c->dScene.release();
@@ -735,7 +761,7 @@ int vpe_set_light(VpeContext* c, const VpeTransform* light, const float gridCent
 
 int vpe_set_displacement_cubemap(VpeContext* c, const uint8_t* r8, int edge) {
     if (!c || !r8 || edge < 1) return fail(c, VPE_E_INVALID_ARG, "bad cubemap");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     size_t n = (size_t)6 * edge * edge;
     std::vector<float> f(n);
     for (size_t i = 0; i < n; i++) f[i] = (float)r8[i] / 255.0f;  // UNORM8 -> float, as the sampler would
@@ -767,7 +793,7 @@ int vpe_set_displacement_cubemap(VpeContext* c, const uint8_t* r8, int edge) {
 
 int vpe_set_light_depth_map(VpeContext* c, const float* depth01) {
     if (!c) return VPE_E_INVALID_ARG;
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     if (!depth01) { c->depthSet = false; return VPE_OK; }
     size_t n = (size_t)c->g.NX * c->g.N * c->g.NY * c->g.N;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -780,7 +806,7 @@ int vpe_set_light_depth_map(VpeContext* c, const float* depth01) {
 int vpe_render_light_depth_map(VpeContext* c, const float* tris, int numTriangles) {
     if (!c || (!tris && numTriangles > 0) || numTriangles < 0) return fail(c, VPE_E_INVALID_ARG, "bad triangle list");
     if (!c->lightSet) return fail(c, VPE_E_NOT_READY, "vpe_set_light has not been called");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     const GridParams& g = c->g;
     DepthRasterParams p;
     p.W2LC = c->w2lc;
@@ -802,7 +828,7 @@ int vpe_render_light_depth_map(VpeContext* c, const float* tris, int numTriangle
 
 int vpe_read_light_depth_map(VpeContext* c, float* depth01) {
     if (!c || !depth01) return VPE_E_INVALID_ARG;
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     const size_t n = (size_t)c->g.NX * c->g.N * c->g.NY * c->g.N;
     if (!c->depthSet) {
@@ -817,7 +843,7 @@ int vpe_set_march_options(VpeContext* c, const VpeMarchOptions* o) {
     if (!c || !o) return VPE_E_INVALID_ARG;
     if (o->targetFormat < 0 || o->targetFormat > 1 || o->debugMode < 0 || o->debugMode > 3) return fail(c, VPE_E_INVALID_ARG, "bad march option");
     if (o->sceneDepth && (o->sceneWidth < 1 || o->sceneHeight < 1)) return fail(c, VPE_E_INVALID_ARG, "bad scene depth size");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     c->targetFormat = o->targetFormat;
     c->debugMode = o->debugMode;
     c->sceneDepthSet = false;
@@ -835,7 +861,7 @@ int vpe_set_march_options(VpeContext* c, const VpeMarchOptions* o) {
 int vpe_composite_scene(VpeContext* c, const float* particles, float* scene, int numPixels, int targetFormat) {
     if (!c || !particles || !scene || numPixels < 0 || targetFormat < 0 || targetFormat > 1) return fail(c, VPE_E_INVALID_ARG, "bad argument");
     if (numPixels == 0) return VPE_OK;
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     CUDA_TRY(c, c->dImage.ensure((size_t)numPixels));
     CUDA_TRY(c, c->dScene.ensure((size_t)numPixels));
     CUDA_TRY(c, cudaMemcpyAsync(c->dImage.p, particles, sizeof(float4) * (size_t)numPixels, cudaMemcpyHostToDevice, c->stream));
@@ -846,9 +872,23 @@ int vpe_composite_scene(VpeContext* c, const float* particles, float* scene, int
     return sync_stream(c);
 }
 
+int vpe_set_debug_options(VpeContext* c, const VpeDebugOptions* o) {
+    if (!c || !o) return VPE_E_INVALID_ARG;
+    if (o->marchKernel < 0 || o->marchKernel > 2 || o->marchBands < 0 || o->marchTileLog2W < 0 || o->marchTileLog2W > 6 || o->linkSpinMs < 0)
+        return fail(c, VPE_E_INVALID_ARG, "bad debug option");
+    const bool layoutChanged = (o->noGray != 0) != (c->dbg.noGray != 0) || (o->noRowPad != 0) != (c->dbg.noRowPad != 0);
+    c->dbg = *o;
+    if (layoutChanged) {  // the brick layout of the next fill changes: the volume of the last fill is gone
+        c->prepared = false;
+        c->filledOnce = false;
+    }
+    rebuild_grid_params(c);
+    return VPE_OK;
+}
+
 int vpe_set_stream(VpeContext* c, void* cudaStream) {
     if (!c) return VPE_E_INVALID_ARG;
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (c->ownStream) cudaStreamDestroy(c->stream);
     c->stream = (cudaStream_t)cudaStream;
@@ -860,7 +900,7 @@ int vpe_fill_prepare(VpeContext* c, const VpeParticle* particles, int n, const V
     if (!c || (!particles && n > 0) || n < 0 || !emitter) return fail(c, VPE_E_INVALID_ARG, "bad particle input");
     if (!c->lightSet) return fail(c, VPE_E_NOT_READY, "vpe_set_light has not been called");
     if (!c->cubeSet) return fail(c, VPE_E_NOT_READY, "vpe_set_displacement_cubemap has not been called");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     const float* dev = reinterpret_cast<const float*>(particles);
     if (!onDevice) {
         CUDA_TRY(c, c->dParticles.ensure((size_t)std::max(n, 1) * 7));
@@ -874,7 +914,7 @@ int vpe_fill_region(VpeContext* c, int x0, int x1, int y0, int y1) {
     if (!c) return VPE_E_INVALID_ARG;
     if (!c->prepared) return fail(c, VPE_E_NOT_READY, "vpe_fill_prepare has not been called");
     if (x0 < 0 || y0 < 0 || x1 > c->g.NX || y1 > c->g.NY || x0 >= x1 || y0 >= y1) return fail(c, VPE_E_INVALID_ARG, "bad region");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     return fill_region_impl(c, x0, x1, y0, y1);
 }
 
@@ -895,7 +935,7 @@ int vpe_fill_device(VpeContext* c, const VpeParticle* particles_dev, int n, cons
 int vpe_fill_density(VpeContext* c) {
     if (!c) return VPE_E_INVALID_ARG;
     if (!c->prepared) return fail(c, VPE_E_NOT_READY, "vpe_fill_prepare has not been called");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     return fill_region_impl(c, 0, c->g.NX, 0, c->g.NY, FILL_DENSITY);
 }
 
@@ -903,7 +943,7 @@ int vpe_fill_sweep_region(VpeContext* c, int x0, int x1, int y0, int y1) {
     if (!c) return VPE_E_INVALID_ARG;
     if (!c->prepared) return fail(c, VPE_E_NOT_READY, "vpe_fill_prepare has not been called");
     if (x0 < 0 || y0 < 0 || x1 > c->g.NX || y1 > c->g.NY || x0 >= x1 || y0 >= y1) return fail(c, VPE_E_INVALID_ARG, "bad region");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     return fill_region_impl(c, x0, x1, y0, y1, FILL_SWEEP);
 }
 
@@ -911,7 +951,7 @@ float* vpe_light_sheet_device(VpeContext* c) { return c ? c->dSheet.p : nullptr;
 
 int vpe_sheet_link_create(VpeContext* c, void* ipcHandle64, void** devPtr) {
     if (!c) return VPE_E_INVALID_ARG;
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     const LinkLayout l = link_layout(c->g);
     if (!c->linkOwn) {
         CUDA_TRY(c, cudaMalloc(&c->linkOwn, l.bytes));
@@ -964,7 +1004,7 @@ int link_map(VpeContext* c, const void* src, int isIpc, void*& out, bool& outIpc
 int vpe_sheet_link_connect(VpeContext* c, const void* upstream, const void* downstream, int handlesAreIpc) {
     if (!c) return VPE_E_INVALID_ARG;
     if (!c->linkOwn) return fail(c, VPE_E_NOT_READY, "vpe_sheet_link_create has not been called");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     link_unmap(c, c->linkUp, c->linkUpIpc);
     link_unmap(c, c->linkDown, c->linkDownIpc);
@@ -977,7 +1017,7 @@ int vpe_fill_sweep_linked(VpeContext* c) {
     if (!c) return VPE_E_INVALID_ARG;
     if (!c->prepared) return fail(c, VPE_E_NOT_READY, "vpe_fill_prepare has not been called");
     if (!c->linkOwn) return fail(c, VPE_E_NOT_READY, "vpe_sheet_link_create has not been called");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     return fill_region_impl(c, 0, c->g.NX, 0, c->g.NY, FILL_SWEEP_LINKED);
 }
 
@@ -985,7 +1025,7 @@ int vpe_sheet_link_status(VpeContext* c, int* timeouts) {
     if (!c || !timeouts) return VPE_E_INVALID_ARG;
     *timeouts = 0;
     if (!c->linkOwn) return VPE_OK;
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     unsigned t = 0;
     CUDA_TRY(c, cudaMemcpy(&t, static_cast<char*>(c->linkOwn) + link_layout(c->g).timeoutOff, sizeof(t), cudaMemcpyDeviceToHost));
@@ -997,7 +1037,7 @@ int vpe_march_device(VpeContext* c, const VpeCamera* cam, float* rgba_dev, int32
     if (!c || !cam || !rgba_dev) return fail(c, VPE_E_INVALID_ARG, "null argument");
     int rc = check_ready_for_march(c);
     if (rc) return rc;
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     return march_impl(c, cam, nullptr, 0, reinterpret_cast<float4*>(rgba_dev), nullptr, samples_dev, false);
 }
 
@@ -1005,14 +1045,14 @@ int vpe_march_partial_device(VpeContext* c, const VpeCamera* cam, float* over_de
     if (!c || !cam || !over_dev || !under_dev) return fail(c, VPE_E_INVALID_ARG, "null argument");
     int rc = check_ready_for_march(c);
     if (rc) return rc;
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     return march_impl(c, cam, nullptr, 0, reinterpret_cast<float4*>(over_dev), reinterpret_cast<float4*>(under_dev), samples_dev, true);
 }
 
 // ---- image link: the slab partial images go straight into the compositing ranks' memory ----
 int vpe_image_link_create(VpeContext* c, int world, int rank, int width, int height, void* ipcHandle64, void** devPtr) {
     if (!c || world < 1 || world > 64 || rank < 0 || rank >= world || width < 1 || height < 1) return fail(c, VPE_E_INVALID_ARG, "bad image link geometry");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (c->imgOwn && (c->imgWorld != world || c->imgRank != rank || c->imgW != width || c->imgH != height)) {
         for (int q = 0; q < 64; q++) {
@@ -1046,7 +1086,7 @@ int vpe_image_link_create(VpeContext* c, int world, int rank, int width, int hei
 int vpe_image_link_connect(VpeContext* c, const void* const* peers, int handlesAreIpc) {
     if (!c || !peers) return VPE_E_INVALID_ARG;
     if (!c->imgOwn) return fail(c, VPE_E_NOT_READY, "vpe_image_link_create has not been called");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     std::vector<float4*> ptrs(c->imgWorld);
     for (int q = 0; q < c->imgWorld; q++) {
@@ -1070,7 +1110,7 @@ int vpe_march_linked(VpeContext* c, const VpeCamera* cam, int32_t* samples_dev) 
     if (rc) return rc;
     if (!c->imgConnected) return fail(c, VPE_E_NOT_READY, "vpe_image_link_connect has not been called");
     if (cam->width != c->imgW || cam->height != c->imgH) return fail(c, VPE_E_INVALID_ARG, "camera image size differs from the image link's");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     c->imgEpoch++;
     // the kernel stores into the receive buffers; rgba/under are placeholders that are never written
     rc = march_impl(c, cam, nullptr, 0, static_cast<float4*>(c->imgOwn), static_cast<float4*>(c->imgOwn), samples_dev, true, nullptr, nullptr, true);
@@ -1084,10 +1124,9 @@ int vpe_march_linked(VpeContext* c, const VpeCamera* cam, int32_t* samples_dev) 
 int vpe_composite_linked(VpeContext* c, float* band_rgba_dev) {
     if (!c || !band_rgba_dev) return fail(c, VPE_E_INVALID_ARG, "null argument");
     if (!c->imgConnected || c->imgEpoch == 0) return fail(c, VPE_E_NOT_READY, "vpe_march_linked has not been called");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     const int np = c->imgPer * c->imgW;
-    const char* ms = getenv("VPE_LINK_SPIN_MS");
-    const long long spin = (long long)(ms ? atof(ms) : 2000.0) * 2000000ll;
+    const long long spin = (long long)(c->dbg.linkSpinMs > 0 ? c->dbg.linkSpinMs : 2000) * 2000000ll;
     char* own = static_cast<char*>(c->imgOwn);
     k_composite_linked<<<div_up(np, 256), 256, 0, c->stream>>>(reinterpret_cast<const float4*>(own), reinterpret_cast<const unsigned*>(own + c->imgFlagsOff),
                                                              c->imgWorld, c->imgPer, c->imgW, (int)(c->imgEpoch & 1u), c->imgEpoch, spin,
@@ -1100,7 +1139,7 @@ int vpe_image_link_status(VpeContext* c, int* timeouts) {
     if (!c || !timeouts) return VPE_E_INVALID_ARG;
     *timeouts = 0;
     if (!c->imgOwn) return VPE_OK;
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     unsigned t = 0;
     CUDA_TRY(c, cudaMemcpy(&t, static_cast<char*>(c->imgOwn) + c->imgTimeoutOff, sizeof(t), cudaMemcpyDeviceToHost));
@@ -1110,7 +1149,7 @@ int vpe_image_link_status(VpeContext* c, int* timeouts) {
 
 int vpe_composite_device(VpeContext* c, const float* const* parts_dev, int numSlabs, int numPixels, float* rgba_dev) {
     if (!c || !parts_dev || numSlabs < 1 || numPixels < 0 || !rgba_dev) return fail(c, VPE_E_INVALID_ARG, "bad argument");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     CUDA_TRY(c, c->dParts.ensure((size_t)2 * numSlabs));
     CUDA_TRY(c, cudaMemcpyAsync(c->dParts.p, parts_dev, sizeof(float4*) * 2 * numSlabs, cudaMemcpyHostToDevice, c->stream));
     if (numPixels > 0)
@@ -1123,7 +1162,7 @@ int vpe_march(VpeContext* c, const VpeCamera* cam, float* rgba, int32_t* samples
     if (!c || !cam || !rgba) return fail(c, VPE_E_INVALID_ARG, "null argument");
     int rc = check_ready_for_march(c);
     if (rc) return rc;
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     const size_t np = (size_t)cam->width * cam->height;
     CUDA_TRY(c, c->dImage.ensure(np));
     if (samples) CUDA_TRY(c, c->dSamples.ensure(np));
@@ -1146,7 +1185,7 @@ int vpe_march_pixels(VpeContext* c, const VpeCamera* cam, const int32_t* pixels,
     const int total = cam->width * cam->height;
     for (int i = 0; i < n; i++)
         if (pixels[i] < 0 || pixels[i] >= total) return fail(c, VPE_E_INVALID_ARG, "pixel index out of range");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     CUDA_TRY(c, c->dPixels.ensure(std::max(n, 1)));
     CUDA_TRY(c, c->dImage.ensure(std::max(n, 1)));
     CUDA_TRY(c, c->dSamples.ensure(std::max(n, 1)));
@@ -1162,7 +1201,7 @@ int vpe_march_footprint(VpeContext* c, const VpeCamera* cam, int64_t* uniqueTexe
     if (!c || !cam || !uniqueTexels) return fail(c, VPE_E_INVALID_ARG, "null argument");
     int rc = check_ready_for_march(c);
     if (rc) return rc;
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     const size_t np = (size_t)cam->width * cam->height;
     const size_t texels = (size_t)c->nCovered * c->g.N * c->g.N * c->g.N;
     const size_t words = texels / 32 + 1;
@@ -1193,7 +1232,7 @@ int vpe_march_footprint(VpeContext* c, const VpeCamera* cam, int64_t* uniqueTexe
 int vpe_read_brick(VpeContext* c, int x, int y, int z, uint16_t* half4, int* covered) {
     if (!c || !covered) return VPE_E_INVALID_ARG;
     if (x < 0 || y < 0 || z < 0 || x >= c->g.NX || y >= c->g.NY || z >= c->g.NZ) return fail(c, VPE_E_INVALID_ARG, "metavoxel index out of range");
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     *covered = 0;
     if (!c->filledOnce) return VPE_OK;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -1219,7 +1258,7 @@ int vpe_read_brick(VpeContext* c, int x, int y, int z, uint16_t* half4, int* cov
 
 int vpe_read_light_sheet(VpeContext* c, float* sheet) {
     if (!c || !sheet) return VPE_E_INVALID_ARG;
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     size_t n = (size_t)c->g.NX * c->g.N * c->g.NY * c->g.N;
     CUDA_TRY(c, cudaMemcpy(sheet, c->dSheet.p, n * sizeof(float), cudaMemcpyDeviceToHost));
@@ -1231,7 +1270,7 @@ int vpe_read_particle_list(VpeContext* c, int x, int y, int z, int32_t* idx, int
     if (x < 0 || y < 0 || z < 0 || x >= c->g.NX || y >= c->g.NY || z >= c->g.NZ) return fail(c, VPE_E_INVALID_ARG, "metavoxel index out of range");
     *n = 0;
     if (!c->prepared) return VPE_OK;
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     int flat = (z * c->g.NY + y) * c->g.NX + x, se[2];
     CUDA_TRY(c, cudaMemcpy(se, c->dCellStart.p + flat, sizeof(int) * 2, cudaMemcpyDeviceToHost));
@@ -1252,7 +1291,7 @@ int vpe_read_metavoxel_position(VpeContext* c, int x, int y, int z, float pos[3]
 
 int vpe_get_stats(VpeContext* c, VpeStats* s) {
     if (!c || !s) return VPE_E_INVALID_ARG;
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope(c->device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (c->fillTimed) {
         cudaEventElapsedTime(&c->stats.fillMs, c->evFill0, c->evFill1);
