@@ -105,6 +105,8 @@ typedef struct VpeStats {
     int64_t brickPoolBytes;
     float fillKernelMs;          /* device time of the per-slice fill kernels alone (last fill)  */
     float marchKernelMs;         /* device time of the march kernel alone (last march)           */
+    int64_t raySamplesSkipped;   /* of raySamples: samples in empty space (all 8 texels of the footprint have density 0)
+                                    that the production march kernels do not fetch; counted by vpe_march_footprint   */
 } VpeStats;
 
 typedef struct VpeContext VpeContext;
@@ -249,7 +251,9 @@ typedef struct VpeDebugOptions {
     int32_t marchBands;     /* host-buffer march: 0 = default (6 bands, copies overlapped), 1 = one launch + one copy, n   */
     int32_t marchTileLog2W; /* warp pixel tile: 0 = default (8x4), else 1 + log2(width): 1 = 1x32 ... 6 = 32x1             */
     int32_t linkSpinMs;     /* sheet / image link: how long a kernel waits for a peer, 0 = default (2000)                  */
-    int32_t reserved[9];
+    int32_t noSweepOverlap; /* 1 = linked sweep after the density pass (one launch on the context's stream) instead of the
+                               persistent sweep kernel that runs concurrently with it                                      */
+    int32_t reserved[8];
 } VpeDebugOptions;
 int vpe_set_debug_options(VpeContext* ctx, const VpeDebugOptions* options);
 

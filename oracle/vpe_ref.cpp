@@ -1241,5 +1241,18 @@ int vpe_ref_num_threads(void) {
     return 1;
 #endif
 }
+// Launchers such as torch.distributed.run export OMP_NUM_THREADS=1; a CPU baseline that claims "all host cores"
+// sets its thread count itself. n <= 0: the number of processors. Returns the count in force.
+int vpe_ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n <= 0) n = omp_get_num_procs();
+    omp_set_dynamic(0);
+    omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 }  // extern "C"

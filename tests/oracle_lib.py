@@ -32,6 +32,8 @@ def load_oracle():
         lib.vpe_ref_f16_to_f32.restype = C.c_float
         lib.vpe_ref_f16_to_f32.argtypes = [C.c_uint16]
         lib.vpe_ref_num_threads.restype = C.c_int
+        lib.vpe_ref_set_num_threads.restype = C.c_int
+        lib.vpe_ref_set_num_threads.argtypes = [C.c_int]
         lib.vpe_ref_march_partial.restype = C.c_int
         lib.vpe_ref_march_partial.argtypes = [P, C.POINTER(_abi.VpeCamera), P, P, P]
         lib.vpe_ref_touched_metavoxels.restype = C.c_int

@@ -53,6 +53,9 @@ class OracleSlabEngine:
     def buffer(self, name, shape):
         return torch.zeros(tuple(shape), dtype=torch.float32)
 
+    def copy_band_to_host(self, band, host_rows):
+        host_rows[...] = band[:host_rows.shape[0]].numpy()
+
     def march_partial(self, camera, padded_rows=None):
         c = _camera(camera)
         rows = max(c.height, padded_rows or c.height)

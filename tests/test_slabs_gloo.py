@@ -117,6 +117,14 @@ def _worker(rank, world, port, out_dir, bands):
         r = slabs.SlabRenderer(eng, dist, fill_bands=bands)
         r.fill(sc["particles"], sc["emitter"])
         img, total = r.march(sc["camera"])
+        # the same frame again, every rank copying its band into one shared host image instead of gathering on rank 0
+        host = slabs.SharedHostImage(dist, sc["camera"]["height"], sc["camera"]["width"])
+        r.march(sc["camera"], count_samples=False, host_image=host)
+        dist.barrier()
+        if rank == 0:
+            assert np.array_equal(host.array, img.numpy()), "shared host image differs from the gathered image"
+        dist.barrier()
+        host.close()
         z0, z1 = eng.slab
         bricks = {}
         for z in range(z0, z1):

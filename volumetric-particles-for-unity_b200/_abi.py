@@ -59,6 +59,7 @@ class VpeStats(C.Structure):
         ("fillMs", C.c_float), ("marchMs", C.c_float),
         ("brickPoolBytes", C.c_int64),
         ("fillKernelMs", C.c_float), ("marchKernelMs", C.c_float),
+        ("raySamplesSkipped", C.c_int64),
     ]
 
 
@@ -70,7 +71,7 @@ class VpeMarchOptions(C.Structure):
 class VpeDebugOptions(C.Structure):
     _fields_ = [("marchKernel", C.c_int32), ("noSkip", C.c_int32), ("noGray", C.c_int32), ("noRowPad", C.c_int32),
                 ("marchBands", C.c_int32), ("marchTileLog2W", C.c_int32), ("linkSpinMs", C.c_int32),
-                ("reserved", C.c_int32 * 9)]
+                ("noSweepOverlap", C.c_int32), ("reserved", C.c_int32 * 8)]
 
 
 assert C.sizeof(VpeParticle) == 28

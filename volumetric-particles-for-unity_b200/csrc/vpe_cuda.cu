@@ -106,6 +106,14 @@ struct VpeContext {
     bool linkUpIpc = false, linkDownIpc = false;
     int linkBlocks = 0;
     unsigned linkEpoch = 0;
+    // linked sweep overlapped with the density pass: per-block "densities in place" flags, a high-priority stream for the
+    // persistent sweep kernel, and the events that order it against the context's stream
+    DevBuf<unsigned> dDensityDone;
+    unsigned densityEpoch = 0;
+    bool densitySignalled = false;   // the density pass of the current fill raises the flags
+    cudaStream_t sweepStream = nullptr;
+    cudaEvent_t evDensityBegin = nullptr, evSweepDone = nullptr;
+    int numSMs = 148;
     // image link (multi-GPU march): receive buffer [2 parities][over|under][slab][row][col] float4 + flags, and
     // every rank's buffer mapped into this process
     void* imgOwn = nullptr;
@@ -115,6 +123,8 @@ struct VpeContext {
     int imgWorld = 0, imgRank = 0, imgW = 0, imgH = 0, imgPer = 0;
     size_t imgFlagsOff = 0, imgTimeoutOff = 0, imgBytes = 0;
     unsigned imgEpoch = 0;
+    unsigned imgKinds = 3;           // partials of the last linked march: bit 0 OVER, bit 1 UNDER
+    bool imgCompositePending = false;  // vpe_march_linked has run, its vpe_composite_linked has not
     bool imgConnected = false;
     // host-path march: bands on two auxiliary streams, each copied home as soon as it is done
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // two compute streams + one copy stream
@@ -344,6 +354,17 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1, FillPhase ph
     a.sheet = c->dSheet.p; a.bricks = c->dBricks.p;
     a.nz = reinterpret_cast<unsigned char*>(c->dNz.p); a.nzRowBytes = c->occRowWords * 4;
     a.x0 = x0; a.x1 = x1; a.y0 = y0; a.y1 = y1;
+    a.densityDone = nullptr; a.densityEpoch = 0;
+    const bool wholeGrid = x0 == 0 && y0 == 0 && x1 == g.NX && y1 == g.NY;
+    if (phase == FILL_DENSITY) {
+        // with a sheet link in place the sweep that follows runs concurrently (k_sweep_overlapped): raise a flag per block
+        c->densitySignalled = c->linkOwn && c->sweepStream && wholeGrid && !c->dbg.noSweepOverlap;
+        if (c->densitySignalled) {
+            a.densityDone = c->dDensityDone.p;
+            a.densityEpoch = ++c->densityEpoch;
+            CUDA_TRY(c, cudaEventRecord(c->evDensityBegin, c->stream));
+        }
+    }
     CUDA_TRY(c, cudaEventRecord(c->evFillK0, c->stream));
     if (phase != FILL_DENSITY) c->bricksGray = g.gray != 0;
     if (c->nCovered > 0 || phase == FILL_SWEEP_LINKED) {  // a linked sweep always runs: its flags must flow
@@ -372,7 +393,19 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1, FillPhase ph
                 }
                 link.epoch = ++c->linkEpoch;
                 link.spinLimit = (long long)(c->dbg.linkSpinMs > 0 ? c->dbg.linkSpinMs : 2000) * 2000000ll;  // ~2 GHz ticks
-                if (g.gray) k_sweep_columns<true, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
+                if (c->densitySignalled) {
+                    // persistent kernel on its own stream, concurrent with the density pass launched just before
+                    a.densityDone = c->dDensityDone.p;
+                    a.densityEpoch = c->densityEpoch;
+                    const int numBlocks = (int)(grid.x * grid.y);
+                    const int ctas = std::min(numBlocks, c->numSMs);
+                    CUDA_TRY(c, cudaStreamWaitEvent(c->sweepStream, c->evDensityBegin, 0));
+                    if (g.gray) k_sweep_overlapped<true><<<ctas, FILLC_THREADS, 0, c->sweepStream>>>(g, a, c->dBrickOf.p, link, (int)grid.x, numBlocks);
+                    else k_sweep_overlapped<false><<<ctas, FILLC_THREADS, 0, c->sweepStream>>>(g, a, c->dBrickOf.p, link, (int)grid.x, numBlocks);
+                    CUDA_TRY(c, cudaEventRecord(c->evSweepDone, c->sweepStream));
+                    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->evSweepDone, 0));
+                    c->densitySignalled = false;
+                } else if (g.gray) k_sweep_columns<true, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
                 else k_sweep_columns<false, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
             } else if (g.gray) k_sweep_columns<true, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
             else k_sweep_columns<false, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
@@ -488,15 +521,20 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     CUDA_TRY(c, cudaEventRecord(c->evMarch0, c->stream));
     c->marchTimed = false;
     CUDA_TRY(c, cudaMemcpyAsync(c->dRank.p, rank.data(), sizeof(int) * rank.size(), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c, cudaMemsetAsync(c->dTotalSamples.p, 0, sizeof(unsigned long long), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->dTotalSamples.p, 0, 2 * sizeof(unsigned long long), c->stream));
     k_mv_camera<<<div_up(c->numCells, 256), 256, 0, c->stream>>>(g, m, c->dBrickOf.p, c->dMvCam.p);
     MarchArgs a;
     a.mvCam = c->dMvCam.p; a.rankAsc = c->dRank.p; a.bricks = c->dBricks.p; a.pixels = pixelsDev;
     a.rgba = rgbaDev; a.under = underDev; a.samples = samplesDev; a.totalSamples = c->dTotalSamples.p;
     a.footprint = footprint;
+    a.totalSkipped = footprint ? c->dTotalSamples.p + 1 : nullptr;
     a.peerRecv = nullptr;
     a.linkWorld = a.linkRank = a.linkPer = a.linkParity = a.linkW = 0;
+    a.linkKinds = 3;
     if (linked) {
+        // a slab entirely on one side of zBoundary has one partial that cannot be anything but zero: it stays at home
+        a.linkKinds = (m.zOverEnd > m.zOverBegin ? 1 : 0) | (m.zUnderEnd > m.zUnderBegin ? 2 : 0);
+        c->imgKinds = (unsigned)a.linkKinds;
         a.peerRecv = c->dImgPeers.p;
         a.linkWorld = c->imgWorld; a.linkRank = c->imgRank; a.linkPer = c->imgPer; a.linkW = c->imgW;
         a.linkParity = (int)(c->imgEpoch & 1u);
@@ -509,7 +547,7 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
         a.orderOf = c->dOrderOf.p;
     }
     const bool skip = !c->dbg.noSkip;
-    a.occ = skip ? c->dOcc.p : nullptr; a.occRowWords = c->occRowWords;
+    a.occ = (skip || footprint) ? c->dOcc.p : nullptr; a.occRowWords = c->occRowWords;
     // Warp pixel tile. Measured on cfg3 (profiles/): the compact 8x4 tile wins over strips that follow
     // the bricks' 128-byte rows, because lanes of a strip sit in different bricks and diverge.
     {
@@ -603,7 +641,7 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     CUDA_TRY(c, cudaEventRecord(c->evMarchK1, c->stream));
     c->stats.marchLaunches = 1 + numBands;
     CUDA_TRY(c, cudaGetLastError());
-    CUDA_TRY(c, cudaMemcpyAsync(c->hTotalSamples, c->dTotalSamples.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->hTotalSamples, c->dTotalSamples.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaEventRecord(c->evMarch1, c->stream));
     c->marchTimed = true;
     c->stats.zBoundary = m.zBoundary;
@@ -674,9 +712,9 @@ int vpe_create(const VpeConfig* cfg, int device, VpeContext** out) {
     ok = ok && c->dBlockSums.ensure(div_up(cells, SCAN_BLOCK)) == cudaSuccess;
     ok = ok && c->dSheet.ensure(sheetN) == cudaSuccess && c->dMvCam.ensure(cells) == cudaSuccess;
     ok = ok && c->dRank.ensure((size_t)c2.numMetavoxelsX * c2.numMetavoxelsY) == cudaSuccess;
-    ok = ok && c->dTotalSamples.ensure(1) == cudaSuccess;
+    ok = ok && c->dTotalSamples.ensure(2) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->hCounts, sizeof(int) * (c2.numMetavoxelsZ + 3)) == cudaSuccess;
-    ok = ok && cudaMallocHost(&c->hTotalSamples, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->hTotalSamples, 2 * sizeof(unsigned long long)) == cudaSuccess;
     if (ok) {
         ok = cudaMemset(c->dBrickOf.p, 0xff, sizeof(int) * cells) == cudaSuccess;
         k_fill_value<<<div_up(sheetN, 256), 256>>>(c->dSheet.p, sheetN, 1.0f);
@@ -687,7 +725,7 @@ int vpe_create(const VpeConfig* cfg, int device, VpeContext** out) {
         vpe_destroy(c);
         return VPE_E_CUDA;
     }
-    *c->hTotalSamples = 0;
+    c->hTotalSamples[0] = c->hTotalSamples[1] = 0;
     *out = c;
     return VPE_OK;
 }
@@ -717,6 +755,10 @@ int vpe_destroy(VpeContext* c) {
     if (c->linkUp && c->linkUpIpc) cudaIpcCloseMemHandle(c->linkUp);
     if (c->linkDown && c->linkDownIpc) cudaIpcCloseMemHandle(c->linkDown);
     if (c->linkOwn) cudaFree(c->linkOwn);
+    c->dDensityDone.release();
+    if (c->sweepStream) cudaStreamDestroy(c->sweepStream);
+    if (c->evDensityBegin) cudaEventDestroy(c->evDensityBegin);
+    if (c->evSweepDone) cudaEventDestroy(c->evSweepDone);
     if (c->hCounts) cudaFreeHost(c->hCounts);
     if (c->hTotalSamples) cudaFreeHost(c->hTotalSamples);
     if (c->evFill0) cudaEventDestroy(c->evFill0);
@@ -958,6 +1000,17 @@ int vpe_sheet_link_create(VpeContext* c, void* ipcHandle64, void** devPtr) {
         CUDA_TRY(c, cudaMemset(c->linkOwn, 0, l.bytes));
         c->linkBlocks = l.blocks;
         c->linkEpoch = 0;
+        CUDA_TRY(c, c->dDensityDone.ensure((size_t)l.blocks));
+        CUDA_TRY(c, cudaMemset(c->dDensityDone.p, 0, sizeof(unsigned) * (size_t)l.blocks));
+        c->densityEpoch = 0;
+        if (!c->sweepStream) {
+            int lo = 0, hi = 0;
+            CUDA_TRY(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUDA_TRY(c, cudaStreamCreateWithPriority(&c->sweepStream, cudaStreamNonBlocking, hi));
+            CUDA_TRY(c, cudaEventCreateWithFlags(&c->evDensityBegin, cudaEventDisableTiming));
+            CUDA_TRY(c, cudaEventCreateWithFlags(&c->evSweepDone, cudaEventDisableTiming));
+            CUDA_TRY(c, cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, c->device));
+        }
     }
     if (ipcHandle64) {
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
@@ -1068,7 +1121,7 @@ int vpe_image_link_create(VpeContext* c, int world, int rank, int width, int hei
         c->imgPer = (height + world - 1) / world;
         const size_t recv = (size_t)2 * 2 * world * c->imgPer * width * sizeof(float4);
         c->imgFlagsOff = (recv + 255) / 256 * 256;
-        c->imgTimeoutOff = c->imgFlagsOff + (size_t)2 * world * sizeof(unsigned);
+        c->imgTimeoutOff = c->imgFlagsOff + (size_t)4 * world * sizeof(unsigned);  // flags[2][world], kinds[2][world]
         c->imgBytes = c->imgTimeoutOff + 256;
         CUDA_TRY(c, cudaMalloc(&c->imgOwn, c->imgBytes));
         CUDA_TRY(c, cudaMemset(c->imgOwn, 0, c->imgBytes));
@@ -1110,14 +1163,18 @@ int vpe_march_linked(VpeContext* c, const VpeCamera* cam, int32_t* samples_dev) 
     if (rc) return rc;
     if (!c->imgConnected) return fail(c, VPE_E_NOT_READY, "vpe_image_link_connect has not been called");
     if (cam->width != c->imgW || cam->height != c->imgH) return fail(c, VPE_E_INVALID_ARG, "camera image size differs from the image link's");
+    // two buffer parities make acknowledgements unnecessary only if every rank composites frame f before it marches frame
+    // f + 1: marching twice in a row could overwrite rows a peer is still compositing
+    if (c->imgCompositePending) return fail(c, VPE_E_NOT_READY, "vpe_march_linked twice without vpe_composite_linked in between");
     DeviceScope deviceScope(c->device);
     c->imgEpoch++;
     // the kernel stores into the receive buffers; rgba/under are placeholders that are never written
     rc = march_impl(c, cam, nullptr, 0, static_cast<float4*>(c->imgOwn), static_cast<float4*>(c->imgOwn), samples_dev, true, nullptr, nullptr, true);
     if (rc) return rc;
-    k_image_signal<<<1, 64, 0, c->stream>>>(c->dImgPeers.p, c->imgFlagsOff, c->imgWorld, c->imgRank, (int)(c->imgEpoch & 1u), c->imgEpoch);
+    k_image_signal<<<1, 64, 0, c->stream>>>(c->dImgPeers.p, c->imgFlagsOff, c->imgWorld, c->imgRank, (int)(c->imgEpoch & 1u), c->imgEpoch, c->imgKinds);
     CUDA_TRY(c, cudaGetLastError());
     c->stats.marchLaunches++;
+    c->imgCompositePending = true;
     return VPE_OK;
 }
 
@@ -1132,6 +1189,7 @@ int vpe_composite_linked(VpeContext* c, float* band_rgba_dev) {
                                                              c->imgWorld, c->imgPer, c->imgW, (int)(c->imgEpoch & 1u), c->imgEpoch, spin,
                                                              reinterpret_cast<unsigned*>(own + c->imgTimeoutOff), reinterpret_cast<float4*>(band_rgba_dev));
     CUDA_TRY(c, cudaGetLastError());
+    c->imgCompositePending = false;
     return VPE_OK;
 }
 
@@ -1222,6 +1280,10 @@ int vpe_march_footprint(VpeContext* c, const VpeCamera* cam, int64_t* uniqueTexe
         *uniqueTexels = (int64_t)h;
     }
     cudaStreamSynchronize(c->stream);
+    if (rc == VPE_OK) {  // the instrumented launch also counted the samples the production kernels skip
+        c->stats.raySamples = (int64_t)c->hTotalSamples[0];
+        c->stats.raySamplesSkipped = (int64_t)c->hTotalSamples[1];
+    }
     bitmap.release();
     count.release();
     c->marchTimed = false;  // an instrumented march is never reported as a timing

@@ -25,8 +25,6 @@ partial rows to the band's owner, which composites them; rank 0 gathers the band
 The engine adapter is what touches memory: `CudaSlabEngine` (below) wraps the CUDA library and
 device tensors; the CPU tests drive the very same `SlabRenderer` with an adapter over the oracle.
 """
-import os
-
 import numpy as np
 
 
@@ -110,7 +108,7 @@ class SlabRenderer:
     """fill() + march() of one rank.  `engine` is a slab engine adapter, `dist` is torch.distributed
     (already initialised) or None for a single process."""
 
-    def __init__(self, engine, dist=None, fill_bands=None):
+    def __init__(self, engine, dist=None, fill_bands=None, image_link=True):
         self.e = engine
         self.dist = dist
         self.rank = dist.get_rank() if dist is not None else 0
@@ -121,12 +119,14 @@ class SlabRenderer:
             raise ValueError("engine owns slab %s, rank %d of %d must own %s" % (engine.slab, self.rank, self.world, (self.z0, self.z1)))
         self.bands = row_bands(gy, fill_bands if fill_bands is not None else default_fill_bands(engine.grid, engine.N, self.world))
         # sheet link: engines that can hand the sheet over through peer memory (CUDA, one node) do so;
-        # fill_bands given explicitly (or VPE_SLAB_NCCL_SWEEP=1) keeps the NCCL send/recv band pipeline
+        # fill_bands given explicitly keeps the NCCL send/recv band pipeline; image_link=False keeps the
+        # NCCL all-to-all of the partial images
         self._image_links = {}
+        self._use_image_link = bool(image_link)
         self.profile = False          # record device times of the density pass and the march kernel (rebalance)
         self._times = None
         self.linked = False
-        if self.world > 1 and fill_bands is None and hasattr(engine, "link_neighbours") and not os.environ.get("VPE_SLAB_NCCL_SWEEP"):
+        if self.world > 1 and fill_bands is None and hasattr(engine, "link_neighbours"):
             self.linked = bool(engine.link_neighbours(dist, self.rank, self.world))
 
     # -- fill -------------------------------------------------------------------------------------
@@ -161,7 +161,7 @@ class SlabRenderer:
 
     def _image_link(self, w, h):
         """Set up (once per image size) the peer-memory exchange of the partial images; False = use NCCL."""
-        if not self.linked or not hasattr(self.e, "image_link_neighbours") or os.environ.get("VPE_SLAB_NCCL_IMAGE"):
+        if not self.linked or not self._use_image_link or not hasattr(self.e, "image_link_neighbours"):
             return False
         key = (w, h)
         if key not in self._image_links:
@@ -201,10 +201,12 @@ class SlabRenderer:
         return slabs_
 
     # -- march ------------------------------------------------------------------------------------
-    def march(self, camera, gather=True, count_samples=True):
+    def march(self, camera, gather=True, count_samples=True, host_image=None):
         """Returns (rgba, total_ray_samples): rgba is the full H x W x 4 image on rank 0 when
         `gather` (None elsewhere), else this rank's band. count_samples=False skips the read-back
-        and all-reduce of the sample counter (a host synchronisation) and returns None for it."""
+        and all-reduce of the sample counter (a host synchronisation) and returns None for it.
+        host_image (a SharedHostImage): every rank copies its band into the shared host image instead of
+        gathering on rank 0's device; the copy is asynchronous, the caller synchronises and barriers."""
         e, d = self.e, self.dist
         h, w = int(camera["height"]), int(camera["width"])
         per = -(-h // self.world)                    # image rows per owner; the image is padded to R * per rows
@@ -230,6 +232,9 @@ class SlabRenderer:
                 parts += [recv_over[s], recv_under[s]]
             band = e.composite(parts, per * w).reshape(per, w, 4)
         total = e.all_reduce_sum(d, samples) if count_samples else None
+        if host_image is not None:
+            e.copy_band_to_host(band, host_image.band())
+            return None, total
         if not gather:
             r0, r1 = image_band(h, self.world, self.rank)
             return band[:r1 - r0], total
@@ -238,6 +243,50 @@ class SlabRenderer:
         if self.rank != 0:
             return None, total
         return full.reshape(self.world * per, w, 4)[:h], total
+
+
+class SharedHostImage:
+    """The frame's H x W x 4 float image in POSIX shared memory, mapped by every rank of the node (and page-locked
+    for CUDA when `pin` is given): each rank copies the band of rows it composited straight home over its own PCIe
+    link, rank 0 reads the whole image after a barrier. Replaces gather-to-rank-0 followed by one big device-to-host
+    copy: R copies of 1/R of the image run in parallel."""
+
+    def __init__(self, dist, height, width, pin=None):
+        from multiprocessing import shared_memory
+        self.dist = dist
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.h, self.w = int(height), int(width)
+        nbytes = self.h * self.w * 16
+        name = [None]
+        if self.rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            name[0] = self.shm.name
+        if dist is not None and self.world > 1:
+            dist.broadcast_object_list(name, src=0)
+        if self.rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+        self.array = np.ndarray((self.h, self.w, 4), dtype=np.float32, buffer=self.shm.buf)
+        self.r0, self.r1 = image_band(self.h, self.world, self.rank)
+        self._pin = pin
+        self._registered = False
+        if pin is not None:                       # pin(address, nbytes) -> True when the pages are locked for the GPU
+            self._registered = bool(pin(self.array.ctypes.data, nbytes))
+
+    def band(self):
+        """This rank's rows of the shared image (a view)."""
+        return self.array[self.r0:self.r1]
+
+    def close(self, unpin=None):
+        if self._registered and unpin is not None:
+            unpin(self.array.ctypes.data)
+        self.array = None
+        try:
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
 
 
 # ------------------------------------------------------------------------------------------------
@@ -397,141 +446,22 @@ class CudaSlabEngine:
     def stats(self):
         return self.eng.stats()
 
+    def link_timeouts(self):
+        """Waits of the sheet link and the image link that gave up (a peer that never arrived): must be 0."""
+        return int(self.eng.sheet_link_timeouts()) + int(self.eng.image_link_timeouts())
 
-# ------------------------------------------------------------------------------------------------
-# bench.py --gpus N (N > 1): strong scaling of BASELINE.json's workload over light-axis slabs
-# ------------------------------------------------------------------------------------------------
-def bench_multi_gpu(args, metric, measured_peak_hbm, ClockSampler):
-    import json
-    import os
-    import time
+    def copy_band_to_host(self, band, host_rows):
+        """Asynchronous device-to-host copy of this rank's composited rows into (pinned, shared) host memory."""
+        t = self.torch
+        dst = t.from_numpy(host_rows)
+        dst.copy_(band[:host_rows.shape[0]], non_blocking=True)
 
-    import torch
-    import torch.distributed as dist
-    from . import scenes
+    @staticmethod
+    def pin_host(address, nbytes):
+        import torch
+        return int(torch.cuda.cudart().cudaHostRegister(address, nbytes, 0)) == 0
 
-    rank, world = dist.get_rank(), dist.get_world_size()
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dev = torch.device("cuda", local_rank)
-    cfg_name = args.config or "cfg3"
-    sc = scenes.make_scene(cfg_name)
-    torch.cuda.set_device(dev)
-    eng = CudaSlabEngine(sc, rank, world, local_rank)
-    r = SlabRenderer(eng, dist, fill_bands=args.fill_bands if getattr(args, "fill_bands", 0) else None)
-    cam = sc["camera"]
-    W, H = cam["width"], cam["height"]
-    n = sc["particles"].shape[0]
-    parts_host = torch.from_numpy(sc["particles"]).pin_memory()
-    parts_dev = parts_host.to(dev)
-
-    def sync():
-        torch.cuda.synchronize(dev)
-        dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def max_over_ranks(x):
-        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t)
-        return float(t.item())
-
-    warm = max(3, args.warmup)
-    slab_list = [slab_range(eng.grid[2], world, q) for q in range(world)]
-    if world > 1 and not getattr(args, "no_rebalance", False):
-        # untimed: measure a frame, move the slab boundaries (SlabRenderer.rebalance), twice
-        for _ in range(2):
-            r.profile = True
-            for _ in range(2):
-                r.fill(parts_dev, sc["emitter"])
-                r.march(cam, gather=False, count_samples=False)
-            slab_list = r.rebalance()
-            r.profile = False
-    for _ in range(warm):
-        r.fill(parts_dev, sc["emitter"])
-        r.march(cam, gather=False)
-    K = max(1, args.steps)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    sync()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    total_samples = 0
-    kern_march, kern_fill = [], []
-    for i in range(K):
-        ev[i][0].record()
-        r.fill(parts_dev, sc["emitter"])
-        ev[i][1].record()
-        r.march(cam, gather=False, count_samples=False)
-        ev[i][2].record()
-    t1.record()
-    sync()
-    _, total_samples = r.march(cam, gather=False)        # untimed: the ray-sample count of the frame
-    kern_march.append(eng.stats()["marchKernelMs"])
-    clk = clocks.stop()
-    total_ms = max_over_ranks(t0.elapsed_time(t1))
-    fill_ms = max_over_ranks(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    march_ms = max_over_ranks(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
-    st = eng.stats()
-    voxels = sum_over_ranks(st["voxelsFilled"])
-    covered = sum_over_ranks(st["numMetavoxelsCovered"])
-    pairs = sum_over_ranks(st["numParticlePairs"])
-    pool = sum_over_ranks(st["brickPoolBytes"])
-    launches = sum_over_ranks((st["fillLaunches"] + st["marchLaunches"] + 1) * K)
-
-    # end to end with HOST buffers: pinned particles in, gathered image out on rank 0
-    rgba_host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
-    e2e = []
-    for i in range(2 + K):
-        sync()
-        a = time.perf_counter()
-        r.fill(parts_host, sc["emitter"])
-        img, _ = r.march(cam, gather=True, count_samples=False)
-        if rank == 0:
-            rgba_host.copy_(img, non_blocking=False)
-        sync()
-        if i >= 2:
-            e2e.append(time.perf_counter() - a)
-    e2e_s = max_over_ranks(float(np.mean(e2e)))
-
-    # roofline of the dominant kernel (march): this rank's compulsory read set / its kernel time
-    peak, peak_src = measured_peak_hbm()
-    uniq = sum_over_ranks(eng.eng.march_footprint(cam))
-    mk = max_over_ranks(float(np.mean(kern_march)))
-    march_bytes = 8.0 * uniq + 2 * 16.0 * W * H * world
-    ach = march_bytes / (mk * 1e-3) / 1e9
-    if rank != 0:
-        return
-    N = eng.N
-    line = {
-        "metric": metric, "value": total_samples / (march_ms * 1e-3), "unit": "ray-samples/s", "n_gpus": world, "steps": K,
-        "warmup": warm, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %d^3 grid x %d^3 voxels, %d particles, %dx%d, %d steps/metavoxel" % (
-            cfg_name, eng.grid[0], N, n, W, H, sc["rayMarchSteps"]),  # same string as bench.workload_name
-            "parallelism": "light-axis slabs x%d (fill: %s; march: slab-local, %s, ordered compositing by screen band)" % (
-                world, "sweep kernel hands the sheet to the next rank over NVLink peer memory, one launch" if r.linked
-                else "sheet rows over NCCL send/recv in %d bands" % len(r.bands),
-                "partials stored into the compositing rank's memory by the march kernel (peer memory + flags)"
-                if r._image_links.get((W, H)) else "NCCL all-to-all of the partial images"),
-            "slabs": [list(x) for x in slab_list],
-            "cache": "inputs larger than L2 (brick pools %.2f GB in total); no flush between iterations" % (pool / 1e9),
-            "covered_metavoxels": int(covered), "particle_metavoxel_pairs": int(pairs)},
-        "fill": {"value": voxels / (fill_ms * 1e-3), "unit": "voxels/s", "ms": fill_ms, "voxels": int(voxels)},
-        "march": {"value": total_samples / (march_ms * 1e-3), "unit": "ray-samples/s", "ms": march_ms, "kernel_ms": mk,
-                  "ray_samples": int(total_samples)},
-        "e2e": {"value": total_samples / e2e_s, "unit": "ray-samples/s", "h2d_bytes_per_step": int(n * 28) * world,
-                "d2h_bytes_per_step": int(W * H * 16), "frame_ms": e2e_s * 1e3,
-                "note": "one fill + one march per step through SlabRenderer with pinned host particles in and the gathered "
-                        "image copied to host on rank 0; value = ray-samples / whole-frame time"},
-        "gpu_launches": int(launches), "clocks": clk,
-        "roofline": {"kernel": "k_march", "bound": "hbm", "achieved": ach, "peak": peak * world, "unit": "GB/s",
-                     "frac": ach / (peak * world), "traffic": None, "peak_source": peak_src + " x n_gpus",
-                     "algorithmic_bytes": march_bytes, "kernel_ms": mk, "distinct_texels": int(uniq)},
-        "cpu_baseline": None,
-    }
-    print(json.dumps(line), flush=True)
+    @staticmethod
+    def unpin_host(address):
+        import torch
+        torch.cuda.cudart().cudaHostUnregister(address)
