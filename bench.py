@@ -117,10 +117,25 @@ def workload_name(cfg_name, sc):
 # The only places of this file that touch oracle/: cpu_sample (the reported CPU baseline / the reference
 # arm) and oracle_pixels (the checker of the image the timed configuration produced).
 # ------------------------------------------------------------------------------------------------
+def host_cores():
+    """Cores this process may use: the affinity mask, capped by a cgroup CPU quota if there is one."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return n
+
+
 def oracle_threads(lib):
-    """torch.distributed.run exports OMP_NUM_THREADS=1 and libgomp is already initialised by then: the oracle's
+    """torch.distributed.run exports OMP_NUM_THREADS=1 and libgomp may already be initialised: the oracle's
     thread count is set explicitly to the number of host cores."""
-    want = os.cpu_count() or 1
+    want = host_cores()
     got = int(lib.vpe_ref_set_num_threads(want))
     assert got == want and (got > 1 or want == 1), "the CPU baseline must use all %d host cores, got %d" % (want, got)
     return got
@@ -219,6 +234,41 @@ def oracle_pixels(cfg_name, image, n_pixels=10000, seed=7):
             "metric": "|gpu - oracle| / max(|oracle|, 1e-2) over RGBA (tests/parity.py)",
             "strict_relative_outlier_frac": float((strict > RTOL).mean()),
             "oracle": "CPU port, parity unpinned by the reference (DESIGN.md 2)", "seconds": time.perf_counter() - t0}
+
+
+def cpu_legs(cfg_name, image, parity_pixels, timeout_s=420):
+    """The CPU legs of the CUDA arm - the reported CPU baseline and the oracle check of the benchmarked image - in CHILD
+    processes with a clean environment (no launcher-imposed OMP_NUM_THREADS, no rank variables) and a time limit, so
+    that neither a launcher's environment nor a slow host can distort or hang the GPU benchmark."""
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "RANK", "LOCAL_RANK", "WORLD_SIZE", "GROUP_RANK",
+                                                            "ROLE_RANK", "LOCAL_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "CUDA_VISIBLE_DEVICES")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    me = os.path.abspath(__file__)
+    cpu, parity = None, None
+    try:
+        out = subprocess.run([sys.executable, me, "--impl", "reference", "--config", cfg_name, "--steps", "1", "--warmup", "0"],
+                             env=env, capture_output=True, text=True, timeout=timeout_s)
+        cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+    except Exception as ex:
+        cpu = {"value": None, "unit": "ray-samples/s", "cores": host_cores(), "kind": "port", "sample": "failed: %r" % (ex,)}
+    fd, path = tempfile.mkstemp(suffix=".npy")
+    os.close(fd)
+    try:
+        np.save(path, np.asarray(image, dtype=np.float32))
+        out = subprocess.run([sys.executable, me, "--check-image", path, "--config", cfg_name, "--parity-pixels", str(parity_pixels)],
+                             env=env, capture_output=True, text=True, timeout=timeout_s)
+        parity = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as ex:
+        parity = {"checked": False, "why": "failed: %r" % (ex,)}
+    finally:
+        os.unlink(path)
+    if parity.get("checked"):
+        assert parity["max_rel_err"] <= parity["tolerance"], "the benchmarked frame differs from the oracle: %r" % parity
+    return cpu, parity
+
+
+def run_check_image(args):
+    print(json.dumps(oracle_pixels(args.config or "cfg3", np.load(args.check_image), args.parity_pixels)), flush=True)
 
 
 def run_reference(args):
@@ -411,11 +461,7 @@ def run_cuda(args):
         legs = general_path_legs(sc, cam, parts_dev, n, local_rank)
     cpu, parity = None, None
     if not args.no_cpu_baseline:
-        r = cpu_sample(cfg_name, 1, 0)
-        cpu = cpu_baseline_entry(r)
-        parity = oracle_pixels(cfg_name, image, args.parity_pixels)
-        if parity.get("checked"):
-            assert parity["max_rel_err"] <= parity["tolerance"], "the benchmarked frame differs from the oracle: %r" % parity
+        cpu, parity = cpu_legs(cfg_name, image, args.parity_pixels)
 
     line = {
         "metric": METRIC, "value": samples / (march_ms * 1e-3), "unit": "ray-samples/s", "n_gpus": 1, "steps": K,
@@ -463,8 +509,8 @@ def run_cuda_slabs(args):
     sc = scenes.make_scene(cfg_name)
     torch.cuda.set_device(dev)
     eng = CudaSlabEngine(sc, rank, world, local_rank)
-    if args.no_sweep_overlap:
-        eng.eng.set_debug_options(no_sweep_overlap=True)
+    eng.debug = dict(sweep_overlap=bool(args.sweep_overlap))
+    eng.profile_slices(False)   # pushes eng.debug to the library
     r = SlabRenderer(eng, dist, fill_bands=args.fill_bands if getattr(args, "fill_bands", 0) else None)
     cam = sc["camera"]
     W, H = cam["width"], cam["height"]
@@ -491,13 +537,15 @@ def run_cuda_slabs(args):
     slab_list = [slab_range(eng.grid[2], world, q) for q in range(world)]
     if not getattr(args, "no_rebalance", False):
         # untimed: measure a frame, move the slab boundaries (SlabRenderer.rebalance), twice
-        for _ in range(2):
+        eng.profile_slices(True)
+        for _ in range(3):
             r.profile = True
             for _ in range(2):
                 r.fill(parts_dev, sc["emitter"])
                 r.march(cam, gather=False, count_samples=False)
             slab_list = r.rebalance()
             r.profile = False
+        eng.profile_slices(False)
     for _ in range(warm):
         r.fill(parts_dev, sc["emitter"])
         r.march(cam, gather=False)
@@ -554,8 +602,11 @@ def run_cuda_slabs(args):
     march_bytes = 8.0 * uniq + 16.0 * W * H * world
     ach = march_bytes / (mk * 1e-3) / 1e9
     host_pinned = bool(host._registered)
+    # rank 0 runs the single-GPU comparison and the CPU legs; the others wait on the rendezvous store (a blocking socket
+    # wait: an NCCL barrier would keep a GPU and a host core spinning next to the CPU baseline)
+    store = dist.distributed_c10d._get_default_store()
     if rank != 0:
-        dist.barrier()   # rank 0 runs the CPU legs and the single-GPU comparison meanwhile
+        store.wait(["vpe_bench_rank0_done"])
         host.close(CudaSlabEngine.unpin_host)
         return
     N = eng.N
@@ -575,13 +626,11 @@ def run_cuda_slabs(args):
     except vpe_b200.VpeError as ex:   # e.g. the whole volume does not fit one GPU next to this rank's slab
         single = {"skipped": str(ex)}
     cpu, parity = None, None
-    if not args.no_cpu_baseline:
-        rr = cpu_sample(cfg_name, 1, 0)
-        cpu = cpu_baseline_entry(rr)
-        parity = oracle_pixels(cfg_name, image, args.parity_pixels)
-        if parity.get("checked"):
-            assert parity["max_rel_err"] <= parity["tolerance"], "the benchmarked frame differs from the oracle: %r" % parity
-    dist.barrier()
+    try:
+        if not args.no_cpu_baseline:
+            cpu, parity = cpu_legs(cfg_name, image, args.parity_pixels)
+    finally:
+        store.set("vpe_bench_rank0_done", "1")
     host.close(CudaSlabEngine.unpin_host)
     fill_bytes = voxels * (8.0 + 8.0 / N)
     line = {
@@ -590,8 +639,8 @@ def run_cuda_slabs(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(cfg_name, sc),
             "parallelism": "light-axis slabs x%d (fill: %s; march: slab-local, %s, ordered compositing by screen band)" % (
-                world, ("persistent sweep kernel concurrent with the density pass, sheet handed to the next rank over NVLink peer memory"
-                        if not args.no_sweep_overlap else "sweep kernel after the density pass, sheet handed to the next rank over NVLink peer memory")
+                world, ("persistent TMA sweep kernel concurrent with the density pass, sheet handed to the next rank over NVLink peer memory"
+                        if args.sweep_overlap else "TMA sweep kernel after the density pass, sheet handed to the next rank over NVLink peer memory")
                 if r.linked else "sheet rows over NCCL send/recv in %d bands" % len(r.bands),
                 "non-zero partials stored into the compositing rank's memory by the march kernel (peer memory + flags)"
                 if r._image_links.get((W, H)) else "NCCL all-to-all of the partial images"),
@@ -610,7 +659,7 @@ def run_cuda_slabs(args):
                      "frac": ach / (peak * world), "traffic": recorded_traffic("k_march"), "peak_source": peak_src + " x n_gpus",
                      "algorithmic_bytes": march_bytes, "kernel_ms": mk, "distinct_texels": int(uniq),
                      "note": "all ranks' compulsory bytes / the slowest rank's kernel time; traffic = the single-GPU ncu capture"},
-        "roofline_fill": {"kernel": "k_fill_columns + k_sweep_overlapped", "bound": "hbm", "achieved": fill_bytes / (fill_ms * 1e-3) / 1e9,
+        "roofline_fill": {"kernel": "k_fill_columns<density> + k_sweep_tma", "bound": "hbm", "achieved": fill_bytes / (fill_ms * 1e-3) / 1e9,
                           "peak": peak * world, "unit": "GB/s", "frac": fill_bytes / (fill_ms * 1e-3) / 1e9 / (peak * world),
                           "traffic": recorded_traffic("k_fill_columns"), "algorithmic_bytes": fill_bytes, "ms": fill_ms,
                           "bytes_per_voxel": 8.0 + 8.0 / N, "note": "whole fill step (bin + density + sweep), slowest rank"},
@@ -631,14 +680,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (baseline sample and the oracle parity check)")
     ap.add_argument("--no-general-paths", action="store_true", help="skip the two extra timed legs of the non-headline kernels (N=1)")
     ap.add_argument("--parity-pixels", type=int, default=10000)
+    ap.add_argument("--check-image", default=None, help="internal: check an H x W x 4 .npy image of --config against the CPU oracle, print JSON")
     ap.add_argument("--march-kernel", type=int, default=0, help="VpeDebugOptions.marchKernel (experiments): 1 = general kernel, 2 = round 1's per-fragment loop")
     ap.add_argument("--tile-log2w", type=int, default=None, help="experiments: warp pixel tile width = 2^n (default 3: 8x4)")
     ap.add_argument("--no-skip", action="store_true", help="experiments: sample every step (ignore the empty-space bitmap)")
     ap.add_argument("--no-rebalance", action="store_true", help="N>1: keep equal slabs (default: balance the slab boundaries during warm-up)")
-    ap.add_argument("--no-sweep-overlap", action="store_true", help="N>1 experiments: linked sweep after the density pass instead of concurrently")
+    ap.add_argument("--sweep-overlap", action="store_true", help="N>1 experiments: linked sweep concurrently with the density pass instead of after it")
     ap.add_argument("--fill-bands", type=int, default=0, help="N>1: row bands of the NCCL fill pipeline (default: the peer-memory sheet link)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.check_image:
+        run_check_image(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_cuda(args)

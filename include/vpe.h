@@ -251,11 +251,19 @@ typedef struct VpeDebugOptions {
     int32_t marchBands;     /* host-buffer march: 0 = default (6 bands, copies overlapped), 1 = one launch + one copy, n   */
     int32_t marchTileLog2W; /* warp pixel tile: 0 = default (8x4), else 1 + log2(width): 1 = 1x32 ... 6 = 32x1             */
     int32_t linkSpinMs;     /* sheet / image link: how long a kernel waits for a peer, 0 = default (2000)                  */
-    int32_t noSweepOverlap; /* 1 = linked sweep after the density pass (one launch on the context's stream) instead of the
-                               persistent sweep kernel that runs concurrently with it                                      */
-    int32_t reserved[8];
+    int32_t sweepOverlap;   /* 1 = the linked sweep runs as a persistent kernel CONCURRENTLY with the density pass (own stream,
+                               per-block flags) instead of after it. Measured (profiles/r02_scaling.md): the particle loop
+                               is issue-bound and loses more than the sweep gains at 8 GPUs, so this is off by default    */
+    int32_t noTmaSweep;     /* 1 = register-staged sweep kernels (k_sweep_columns / k_sweep_overlapped) instead of the TMA pipeline  */
+    int32_t profileSlices;  /* 1 = keep per-slice work figures of the fills and marches that follow (vpe_read_slice_profile)        */
+    int32_t reserved[6];
 } VpeDebugOptions;
 int vpe_set_debug_options(VpeContext* ctx, const VpeDebugOptions* options);
+/* Work per light-axis slice of the last fill / march of this context (NZ entries each, NULL = not wanted; slices outside the
+ * context's slab are 0): (particle, metavoxel) pairs and covered metavoxels of the fill, ray samples of the march. The slab
+ * renderer balances the slab boundaries with them (VPR.cs:505 walks the slices in order; their cost is far from uniform).
+ * Needs VpeDebugOptions.profileSlices; the oracle returns VPE_E_UNSUPPORTED. */
+int vpe_read_slice_profile(VpeContext* ctx, int64_t* pairs, int64_t* coveredMetavoxels, int64_t* raySamples);
 
 /* ---- measurement ----
  * Number of distinct volume texels in the union of all samples' 8-texel trilinear footprints for

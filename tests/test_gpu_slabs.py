@@ -285,3 +285,84 @@ def test_nccl_two_ranks(tmp_path):
     img_ref, smp_ref = ref.march(sc["camera"])
     assert int(out["total"]) == int(smp_ref.sum())
     assert max_rel_err(out["img"], img_ref) <= RTOL
+
+
+def test_overlapped_sweep_many_blocks_back_to_back_frames():
+    """The persistent sweep kernel (k_sweep_overlapped) runs concurrently with the density pass of the same fill. With more
+    blocks of voxel columns than SMs every sweep CTA takes several blocks; several frames are enqueued without a host
+    synchronisation in between, as bench.py does. Two contexts share the GPU; result: the single-context volume, bit for bit."""
+    import torch
+    sc = scenes.make_scene("cfg1", image=(64, 48))
+    sc["grid"] = (10, 9, 4)
+    sc["numVoxels"] = 32
+    rng = np.random.default_rng(5)
+    n = 160
+    p = np.zeros((n, 7), dtype=np.float32)
+    p[:, 0:3] = rng.uniform(-3.5, 3.5, size=(n, 3)) * np.array([1.0, 1.0, 0.4])
+    p[:, 3] = rng.uniform(1.2, 2.4, size=n)
+    p[:, 4] = rng.uniform(0, 360, size=n)
+    p[:, 5] = rng.uniform(0.1, 6.0, size=n)
+    p[:, 6] = 6.0
+    sc["particles"] = p
+    one = vpe_b200.engine_for_scene(None, sc)
+    scenes.apply_scene(one, sc)
+    one.fill(sc["particles"], sc["emitter"])
+    assert one.stats()["numMetavoxelsCovered"] > 100
+    ranks = [slabs.CudaSlabEngine(sc, r, 2, 0) for r in range(2)]
+    for e in ranks:
+        e.eng.set_debug_options(link_spin_ms=300, sweep_overlap=True)
+    ptrs = [e.eng.sheet_link_create()[1] for e in ranks]
+    ranks[0].eng.sheet_link_connect(None, ptrs[1])
+    ranks[1].eng.sheet_link_connect(ptrs[0], None)
+    for frame in range(4):
+        for e in ranks:
+            e.fill_prepare(sc["particles"], sc["emitter"])
+            e.fill_density()
+            e.fill_sweep_linked()
+    torch.cuda.synchronize()
+    for e in ranks:
+        assert e.eng.sheet_link_timeouts() == 0, e.eng.lib.vpe_last_error(e.eng._ctx)
+    assert np.array_equal(ranks[1].eng.read_light_sheet(), one.read_light_sheet())
+    gx, gy, gz = ranks[0].grid
+    for z in range(gz):
+        owner = ranks[0] if z < ranks[0].slab[1] else ranks[1]
+        for y in range(gy):
+            for x in range(gx):
+                a, b = one.read_brick(x, y, z), owner.eng.read_brick(x, y, z)
+                assert (a is None) == (b is None)
+                if a is not None:
+                    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n_vox,tma", [(32, True), (64, True), (32, False)])
+def test_density_plus_sweep_equals_the_fused_fill(n_vox, tma):
+    """vpe_fill_density + vpe_fill_sweep_region == vpe_fill, bit for bit, for the brick sizes the TMA sweep pipeline
+    (k_sweep_tma: cp.async.bulk.tensor loads/stores of [8 slices][rows][N] boxes, mbarrier ring) handles, and for the
+    register-staged kernel it replaces (VpeDebugOptions.noTmaSweep)."""
+    sc = scenes.make_scene("cfg1", image=(32, 32))
+    sc["grid"] = (3, 2, 3)
+    sc["numVoxels"] = n_vox
+    a = vpe_b200.engine_for_scene(None, sc)
+    b = vpe_b200.engine_for_scene(None, sc)
+    if not tma:
+        b.set_debug_options(no_tma_sweep=True)
+    for e in (a, b):
+        scenes.apply_scene(e, sc)
+    p = sc["particles"].copy()
+    p[:, 0:3] *= 0.35
+    a.fill(p, sc["emitter"])
+    for frame in range(2):
+        b.fill_prepare(p, sc["emitter"])
+        b.fill_density()
+        b.fill_sweep_region(0, 3, 0, 2)
+    assert np.array_equal(a.read_light_sheet(), b.read_light_sheet())
+    cov = 0
+    for z in range(3):
+        for y in range(2):
+            for x in range(3):
+                ba, bb = a.read_brick(x, y, z), b.read_brick(x, y, z)
+                assert (ba is None) == (bb is None)
+                if ba is not None:
+                    cov += 1
+                    assert np.array_equal(ba, bb), (x, y, z)
+    assert cov >= 4

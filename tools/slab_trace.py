@@ -13,10 +13,20 @@ rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 sc = scenes.make_scene(sys.argv[1] if len(sys.argv) > 1 else "cfg3")
+mode = sys.argv[2] if len(sys.argv) > 2 else "nooverlap"      # overlap | nooverlap | regsweep
 eng = slabs.CudaSlabEngine(sc, rank, world, lr)
+eng.debug = dict(sweep_overlap=(mode == "overlap"), no_tma_sweep=(mode == "regsweep"))
 r = slabs.SlabRenderer(eng, dist)
 cam = sc["camera"]
 parts = torch.from_numpy(sc["particles"]).cuda()
+eng.profile_slices(True)
+for _ in range(3):   # the bench's warm-up: balance the slabs
+    r.profile = True
+    for _ in range(2):
+        r.fill(parts, sc["emitter"]); r.march(cam, gather=False, count_samples=False)
+    slab_list = r.rebalance()
+    r.profile = False
+eng.profile_slices(False)
 for _ in range(3):
     r.fill(parts, sc["emitter"]); r.march(cam, gather=False, count_samples=False)
 e, d = r.e, dist
@@ -32,20 +42,15 @@ for rep in range(2):
     e.fill_prepare(parts, sc["emitter"]); mark("prepare")
     e.fill_density(); mark("density")
     e.fill_sweep_linked(); mark("sweep")
-    over, under = e.march_partial(cam, per * world); mark("march_k")
-    ro = e.buffer("recv_over", (world, per, w, 4)); ru = e.buffer("recv_under", (world, per, w, 4))
-    d.all_to_all_single(ro.view(-1), over.view(-1)); mark("a2a_over")
-    d.all_to_all_single(ru.view(-1), under.view(-1)); mark("a2a_under")
-    ps = []
-    for s in range(world):
-        ps += [ro[s], ru[s]]
-    e.composite(ps, per * w); mark("composite")
+    e.march_linked(cam); mark("march")
+    e.composite_linked(per, w); mark("composite")
     torch.cuda.synchronize()
     h1 = time.perf_counter()
     for rr in range(world):
         dist.barrier()
         if rr == rank and rep == 1:
             st = e.stats()
-            print("rank %d host %.2f ms | fillK %.2f marchK %.2f | " % (rank, (h1 - h0) * 1e3, st["fillKernelMs"], st["marchKernelMs"]) +
-                  " ".join("%s:%.2f(h%.2f)" % (t, ev[0][1].elapsed_time(x), (ht - h0) * 1e3) for (t, x, ht) in ev[1:]), flush=True)
+            print("%s rank %d slab %s host %.2f ms | marchK %.2f | " % (mode, rank, e.slab, (h1 - h0) * 1e3, st["marchKernelMs"]) +
+                  " ".join("%s:%.2f" % (t, ev[0][1].elapsed_time(x)) for (t, x, ht) in ev[1:]), flush=True)
+assert e.link_timeouts() == 0
 dist.destroy_process_group()

@@ -71,7 +71,7 @@ class VpeMarchOptions(C.Structure):
 class VpeDebugOptions(C.Structure):
     _fields_ = [("marchKernel", C.c_int32), ("noSkip", C.c_int32), ("noGray", C.c_int32), ("noRowPad", C.c_int32),
                 ("marchBands", C.c_int32), ("marchTileLog2W", C.c_int32), ("linkSpinMs", C.c_int32),
-                ("noSweepOverlap", C.c_int32), ("reserved", C.c_int32 * 8)]
+                ("sweepOverlap", C.c_int32), ("noTmaSweep", C.c_int32), ("profileSlices", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 assert C.sizeof(VpeParticle) == 28
@@ -91,6 +91,7 @@ PROTOTYPES = {
     "vpe_read_light_depth_map": (C.c_int, [_P, _P]),
     "vpe_set_march_options": (C.c_int, [_P, C.POINTER(VpeMarchOptions)]),
     "vpe_set_debug_options": (C.c_int, [_P, C.POINTER(VpeDebugOptions)]),
+    "vpe_read_slice_profile": (C.c_int, [_P, _P, _P, _P]),
     "vpe_composite_scene": (C.c_int, [_P, _P, _P, C.c_int, C.c_int]),
     "vpe_fill": (C.c_int, [_P, _P, C.c_int, C.POINTER(VpeTransform)]),
     "vpe_march": (C.c_int, [_P, C.POINTER(VpeCamera), _P, _P]),

@@ -97,6 +97,8 @@ struct VpeContext {
     DevBuf<int> dRank, dPixels, dSamples;
     DevBuf<float4> dImage, dImage2;
     DevBuf<unsigned long long> dTotalSamples;
+    DevBuf<unsigned long long> dSliceSamples;   // [NZ] ray samples per slice of the last march (VpeDebugOptions.profileSlices)
+    std::vector<int> slicePairs;                // [NZ + 1] prefix of (particle, metavoxel) pairs per slice of the last fill
     DevBuf<const float4*> dParts;
     // sheet link (multi-GPU sweep over peer memory): own buffer [inbox | flagIn | ackIn | timeouts] and the
     // neighbours' buffers mapped into this process
@@ -114,6 +116,12 @@ struct VpeContext {
     cudaStream_t sweepStream = nullptr;
     cudaEvent_t evDensityBegin = nullptr, evSweepDone = nullptr;
     int numSMs = 148;
+    // brick pool as a TMA tensor (x, y, z, brick) of 8-byte texels, for k_sweep_tma; re-encoded when the pool moves
+    CUtensorMap brickMap;
+    const void* brickMapBase = nullptr;
+    size_t brickMapBricks = 0;
+    int brickMapRowStride = 0;
+    bool brickMapOk = false;
     // image link (multi-GPU march): receive buffer [2 parities][over|under][slab][row][col] float4 + flags, and
     // every rank's buffer mapped into this process
     void* imgOwn = nullptr;
@@ -251,6 +259,70 @@ int sync_stream(VpeContext* c) {
 }
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+#ifndef VPE_TMA_STAGES_OVERLAP
+#define VPE_TMA_STAGES_OVERLAP 3
+#endif
+#ifndef VPE_TMA_STAGES_ALONE
+#define VPE_TMA_STAGES_ALONE 4
+#endif
+constexpr int TMA_STAGES_OVERLAP = VPE_TMA_STAGES_OVERLAP, TMA_STAGES_ALONE = VPE_TMA_STAGES_ALONE;  // shared-memory stages of k_sweep_tma (16 KB each)
+
+// CUDA loads kernels lazily, and loading one may wait until the device is idle. This library runs kernels that spin on
+// flags raised by other kernels (sheet link, image link, the overlapped sweep): if the producer is a kernel that still has
+// to be loaded while the consumer already spins, the load waits for the consumer and the consumer for the producer. Every
+// kernel is therefore loaded when the first context of a device is created, before anything can spin.
+template <class K>
+void preload(K kernel) {
+    cudaFuncAttributes at;
+    if (cudaFuncGetAttributes(&at, kernel) != cudaSuccess) cudaGetLastError();
+}
+// Kernels that wait on flags raised by other kernels of the same GPU must be able to share an SM with the producer. The
+// shared-memory / L1 split of an SM can only change while the SM is idle: a resident spinning CTA of a kernel that asked for
+// "no shared memory" would keep every CTA of a producer that needs shared memory (k_fill_columns: 36 KB) off its SM - on all
+// SMs at once for a persistent kernel, i.e. for as long as it spins. All of them therefore ask for the same carve-out.
+template <class K>
+void prefer_max_shared(K kernel) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) != cudaSuccess) cudaGetLastError();
+}
+template <int NT>
+void preload_march() {
+#define VPE_PRELOAD_MARCH(S, G, P) preload(k_march_flat<NT, S, G, P>); preload(k_march<NT, false, S, G, P>);
+    VPE_PRELOAD_MARCH(false, false, false) VPE_PRELOAD_MARCH(false, false, true) VPE_PRELOAD_MARCH(false, true, false) VPE_PRELOAD_MARCH(false, true, true)
+    VPE_PRELOAD_MARCH(true, false, false) VPE_PRELOAD_MARCH(true, false, true) VPE_PRELOAD_MARCH(true, true, false) VPE_PRELOAD_MARCH(true, true, true)
+#undef VPE_PRELOAD_MARCH
+}
+void preload_kernels(int device) {
+    static bool done[64] = {};
+    if (device < 0 || device >= 64 || done[device]) return;
+    done[device] = true;
+    preload(k_particle_setup); preload(k_scatter_pairs); preload(k_sort_lists); preload(k_scan_reduce); preload(k_scan_blocks);
+    preload(k_scan_final); preload(k_fill_value); preload(k_occ_build); preload(k_mv_camera); preload(k_popcount);
+    preload(k_fill_columns<false, false>); preload(k_fill_columns<false, true>); preload(k_fill_columns<true, false>);
+    preload(k_sweep_columns<false, false>); preload(k_sweep_columns<true, false>); preload(k_sweep_columns<false, true>);
+    preload(k_sweep_columns<true, true>); preload(k_sweep_overlapped<false>); preload(k_sweep_overlapped<true>);
+    preload_march<0>(); preload_march<32>(); preload_march<64>();
+    preload(k_march<-1, true, false, false, false>); preload(k_march<-1, false, false, false, false>);
+    preload(k_image_signal); preload(k_composite_linked); preload(k_composite); preload(k_raster_depth);
+    preload(k_composite_scene); preload(k_order_index);
+    prefer_max_shared(k_fill_columns<false, false>); prefer_max_shared(k_fill_columns<false, true>); prefer_max_shared(k_fill_columns<true, false>);
+    prefer_max_shared(k_sweep_columns<false, true>); prefer_max_shared(k_sweep_columns<true, true>);
+    prefer_max_shared(k_sweep_overlapped<false>); prefer_max_shared(k_sweep_overlapped<true>);
+    prefer_max_shared(k_composite_linked); prefer_max_shared(k_occ_build);
+#define VPE_TMA_ATTR(NT, GRAY, LINKED, OVERLAP)                                                                                          \
+    {                                                                                                                                   \
+        constexpr int ST = OVERLAP ? TMA_STAGES_OVERLAP : TMA_STAGES_ALONE;                                                             \
+        auto k = k_sweep_tma<NT, GRAY, LINKED, OVERLAP, ST>;                                                                            \
+        preload(k);                                                                                                                     \
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, ST * TMA_S * FILLC_THREADS * 8) != cudaSuccess) cudaGetLastError(); \
+        prefer_max_shared(k);                                                                                                           \
+    }
+#define VPE_TMA_ATTR4(NT, GRAY) VPE_TMA_ATTR(NT, GRAY, false, false) VPE_TMA_ATTR(NT, GRAY, true, false) VPE_TMA_ATTR(NT, GRAY, true, true)
+    VPE_TMA_ATTR4(32, false) VPE_TMA_ATTR4(32, true) VPE_TMA_ATTR4(64, false) VPE_TMA_ATTR4(64, true)
+#undef VPE_TMA_ATTR4
+#undef VPE_TMA_ATTR
+}
+
+void update_brick_map(VpeContext* c);
 
 // ---- fill -------------------------------------------------------------------------------------
 int fill_prepare_impl(VpeContext* c, const float* particlesDev, int n, const VpeTransform* em) {
@@ -281,6 +353,11 @@ int fill_prepare_impl(VpeContext* c, const float* particlesDev, int n, const Vpe
     CUDA_TRY(c, cudaMemcpyAsync(c->hCounts + g.NZ + 1, c->dTotals.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->sliceStart.assign(c->hCounts, c->hCounts + g.NZ + 1);
+    if (c->dbg.profileSlices) {  // pairs before each slice = cellStart at the slice's first cell (load balancing of the slabs)
+        c->slicePairs.assign((size_t)g.NZ + 1, 0);
+        CUDA_TRY(c, cudaMemcpy2D(c->slicePairs.data(), sizeof(int), c->dCellStart.p, sizeof(int) * (size_t)g.NX * g.NY, sizeof(int), (size_t)g.NZ + 1,
+                                 cudaMemcpyDeviceToHost));
+    }
     c->nPairs = c->hCounts[g.NZ + 1];
     c->nCovered = c->hCounts[g.NZ + 2];
     c->nParticles = n;
@@ -305,6 +382,7 @@ int fill_prepare_impl(VpeContext* c, const float* particlesDev, int n, const Vpe
             return fail(c, VPE_E_OUT_OF_MEMORY, "brick pool does not fit in device memory");
         }
     }
+    update_brick_map(c);
     {
         // empty-space bitmaps: every word of a covered brick is rewritten by each fill (k_fill_columns / k_occ_build)
         const size_t words = std::max<size_t>(1, (size_t)c->nCovered * g.N * g.N * c->occRowWords);
@@ -328,6 +406,53 @@ int fill_prepare_impl(VpeContext* c, const float* particlesDev, int n, const Vpe
 }
 
 enum FillPhase { FILL_FUSED, FILL_DENSITY, FILL_SWEEP, FILL_SWEEP_LINKED };
+
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+        else cudaGetLastError();
+    }
+    return fn;
+}
+
+// The brick pool as the tensor k_sweep_tma moves: box = one block of voxel columns (N x 256/N) x TMA_S slices of one brick.
+void update_brick_map(VpeContext* c) {
+    const GridParams& g = c->g;
+    const size_t brickTexels = (size_t)g.N * g.N * g.rowStride;
+    const size_t bricks = brickTexels ? c->dBricks.cap / brickTexels : 0;
+    if (c->brickMapOk && c->brickMapBase == c->dBricks.p && c->brickMapBricks == bricks && c->brickMapRowStride == g.rowStride) return;
+    c->brickMapOk = false;
+    c->brickMapBase = c->dBricks.p; c->brickMapBricks = bricks; c->brickMapRowStride = g.rowStride;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || bricks == 0 || (g.N != 32 && g.N != 64) || (g.rowStride * 8) % 16 != 0) return;
+    const cuuint64_t dims[4] = {(cuuint64_t)g.rowStride, (cuuint64_t)g.N, (cuuint64_t)g.N, (cuuint64_t)bricks};
+    const cuuint64_t strides[3] = {(cuuint64_t)g.rowStride * 8, (cuuint64_t)g.N * g.rowStride * 8, (cuuint64_t)brickTexels * 8};
+    const cuuint32_t box[4] = {(cuuint32_t)g.N, (cuuint32_t)(FILLC_THREADS / g.N), (cuuint32_t)TMA_S, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    c->brickMapOk = enc(&c->brickMap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, c->dBricks.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <bool LINKED, bool OVERLAP>
+void launch_sweep_tma(VpeContext* c, const FillArgs& a, const SheetLink& link, dim3 grid, cudaStream_t st) {
+    const GridParams& g = c->g;
+    constexpr int STAGES = OVERLAP ? TMA_STAGES_OVERLAP : TMA_STAGES_ALONE;
+    const size_t smem = (size_t)STAGES * TMA_S * FILLC_THREADS * 8;
+    const int numBlocks = (int)(grid.x * grid.y);
+    const int ctas = OVERLAP ? std::min(numBlocks, c->numSMs) : numBlocks;
+#define VPE_SWEEP_TMA(NT, GRAY) k_sweep_tma<NT, GRAY, LINKED, OVERLAP, STAGES><<<ctas, FILLC_THREADS, smem, st>>>(c->brickMap, g, a, c->dBrickOf.p, link, (int)grid.x, numBlocks)
+    if (g.N == 32) { if (g.gray) VPE_SWEEP_TMA(32, true); else VPE_SWEEP_TMA(32, false); }
+    else { if (g.gray) VPE_SWEEP_TMA(64, true); else VPE_SWEEP_TMA(64, false); }
+#undef VPE_SWEEP_TMA
+}
 
 // Layout of a sheet link buffer; identical on every rank (same grid and voxel count).
 struct LinkLayout {
@@ -358,7 +483,7 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1, FillPhase ph
     const bool wholeGrid = x0 == 0 && y0 == 0 && x1 == g.NX && y1 == g.NY;
     if (phase == FILL_DENSITY) {
         // with a sheet link in place the sweep that follows runs concurrently (k_sweep_overlapped): raise a flag per block
-        c->densitySignalled = c->linkOwn && c->sweepStream && wholeGrid && !c->dbg.noSweepOverlap;
+        c->densitySignalled = c->linkOwn && c->sweepStream && wholeGrid && c->dbg.sweepOverlap != 0;
         if (c->densitySignalled) {
             a.densityDone = c->dDensityDone.p;
             a.densityEpoch = ++c->densityEpoch;
@@ -393,6 +518,7 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1, FillPhase ph
                 }
                 link.epoch = ++c->linkEpoch;
                 link.spinLimit = (long long)(c->dbg.linkSpinMs > 0 ? c->dbg.linkSpinMs : 2000) * 2000000ll;  // ~2 GHz ticks
+                const bool tma = c->brickMapOk && !c->dbg.noTmaSweep;
                 if (c->densitySignalled) {
                     // persistent kernel on its own stream, concurrent with the density pass launched just before
                     a.densityDone = c->dDensityDone.p;
@@ -400,19 +526,22 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1, FillPhase ph
                     const int numBlocks = (int)(grid.x * grid.y);
                     const int ctas = std::min(numBlocks, c->numSMs);
                     CUDA_TRY(c, cudaStreamWaitEvent(c->sweepStream, c->evDensityBegin, 0));
-                    if (g.gray) k_sweep_overlapped<true><<<ctas, FILLC_THREADS, 0, c->sweepStream>>>(g, a, c->dBrickOf.p, link, (int)grid.x, numBlocks);
+                    if (tma) launch_sweep_tma<true, true>(c, a, link, grid, c->sweepStream);
+                    else if (g.gray) k_sweep_overlapped<true><<<ctas, FILLC_THREADS, 0, c->sweepStream>>>(g, a, c->dBrickOf.p, link, (int)grid.x, numBlocks);
                     else k_sweep_overlapped<false><<<ctas, FILLC_THREADS, 0, c->sweepStream>>>(g, a, c->dBrickOf.p, link, (int)grid.x, numBlocks);
                     CUDA_TRY(c, cudaEventRecord(c->evSweepDone, c->sweepStream));
                     CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->evSweepDone, 0));
                     c->densitySignalled = false;
-                } else if (g.gray) k_sweep_columns<true, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
+                } else if (tma) launch_sweep_tma<true, false>(c, a, link, grid, c->stream);
+                else if (g.gray) k_sweep_columns<true, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
                 else k_sweep_columns<false, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
-            } else if (g.gray) k_sweep_columns<true, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
+            } else if (c->brickMapOk && !c->dbg.noTmaSweep) launch_sweep_tma<false, false>(c, a, link, grid, c->stream);
+            else if (g.gray) k_sweep_columns<true, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
             else k_sweep_columns<false, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
         }
         c->stats.fillLaunches++;
         if ((phase == FILL_FUSED || phase == FILL_DENSITY) && c->nCovered > 0) {  // the densities are final: derive the march's bitmap
-            k_occ_build<<<dim3((x1 - x0) * (y1 - y0), g.z1 - g.z0), 256, 0, c->stream>>>(g, c->dBrickOf.p, c->dNz.p, c->dOcc.p, c->occRowWords, x0, x1, y0);
+            k_occ_build<<<(x1 - x0) * (y1 - y0), 256, 0, c->stream>>>(g, c->dBrickOf.p, c->dNz.p, c->dOcc.p, c->occRowWords, x0, x1, y0);
             c->stats.fillLaunches++;
         }
     }
@@ -528,6 +657,12 @@ int march_impl(VpeContext* c, const VpeCamera* cam, const int* pixelsDev, int nP
     a.rgba = rgbaDev; a.under = underDev; a.samples = samplesDev; a.totalSamples = c->dTotalSamples.p;
     a.footprint = footprint;
     a.totalSkipped = footprint ? c->dTotalSamples.p + 1 : nullptr;
+    a.sliceSamples = nullptr;
+    if (c->dbg.profileSlices && !footprint) {
+        CUDA_TRY(c, c->dSliceSamples.ensure((size_t)g.NZ));
+        CUDA_TRY(c, cudaMemsetAsync(c->dSliceSamples.p, 0, sizeof(unsigned long long) * (size_t)g.NZ, c->stream));
+        a.sliceSamples = c->dSliceSamples.p;
+    }
     a.peerRecv = nullptr;
     a.linkWorld = a.linkRank = a.linkPer = a.linkParity = a.linkW = 0;
     a.linkKinds = 3;
@@ -689,6 +824,7 @@ int vpe_create(const VpeConfig* cfg, int device, VpeContext** out) {
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return VPE_E_CUDA;  // no fallback
     DeviceScope deviceScope(device);
     if (!deviceScope.ok) { cudaGetLastError(); return VPE_E_CUDA; }
+    preload_kernels(device);
     VpeContext* c = new VpeContext();
     c->cfg = c2;
     c->device = device;
@@ -739,7 +875,7 @@ int vpe_destroy(VpeContext* c) {
     c->dSliceStart.release(); c->dPairs.release(); c->dTotals.release(); c->dBlockSums.release();
     c->dCube.release(); c->dCubeFp.release(); c->dDepth.release(); c->dSheet.release(); c->dBricks.release(); c->dNz.release(); c->dOcc.release(); c->dMvCam.release();
     c->dRank.release(); c->dPixels.release(); c->dSamples.release(); c->dImage.release(); c->dImage2.release();
-    c->dTotalSamples.release(); c->dParts.release();
+    c->dTotalSamples.release(); c->dSliceSamples.release(); c->dParts.release();
     c->dSceneDepth.release(); c->dOrderOf.release(); c->dTris.release(); c->dScene.release();
     for (int i = 0; i < 3; i++) {
         if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
@@ -1080,9 +1216,14 @@ int vpe_sheet_link_status(VpeContext* c, int* timeouts) {
     if (!c->linkOwn) return VPE_OK;
     DeviceScope deviceScope(c->device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    unsigned t = 0;
-    CUDA_TRY(c, cudaMemcpy(&t, static_cast<char*>(c->linkOwn) + link_layout(c->g).timeoutOff, sizeof(t), cudaMemcpyDeviceToHost));
-    *timeouts = (int)t;
+    unsigned t[4] = {0, 0, 0, 0};  // total, density-flag waits, upstream waits, acknowledge waits
+    CUDA_TRY(c, cudaMemcpy(t, static_cast<char*>(c->linkOwn) + link_layout(c->g).timeoutOff, sizeof(t), cudaMemcpyDeviceToHost));
+    *timeouts = (int)t[0];
+    if (t[0]) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "sheet link waits that gave up: %u (own densities %u, upstream sheet %u, downstream acknowledge %u)", t[0], t[1], t[2], t[3]);
+        c->err = buf;
+    }
     return VPE_OK;
 }
 
@@ -1348,6 +1489,24 @@ int vpe_read_metavoxel_position(VpeContext* c, int x, int y, int z, float pos[3]
     if (x < 0 || y < 0 || z < 0 || x >= c->g.NX || y >= c->g.NY || z >= c->g.NZ) return fail(c, VPE_E_INVALID_ARG, "metavoxel index out of range");
     F3 p = mv_center(c->g, x, y, z);  // same routine the kernels call
     pos[0] = p.x; pos[1] = p.y; pos[2] = p.z;
+    return VPE_OK;
+}
+
+int vpe_read_slice_profile(VpeContext* c, int64_t* pairs, int64_t* covered, int64_t* samples) {
+    if (!c) return VPE_E_INVALID_ARG;
+    if (!c->dbg.profileSlices) return fail(c, VPE_E_NOT_READY, "VpeDebugOptions.profileSlices is off");
+    DeviceScope deviceScope(c->device);
+    const int NZ = c->g.NZ;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int z = 0; z < NZ; z++) {
+        if (pairs) pairs[z] = (c->prepared && (int)c->slicePairs.size() == NZ + 1) ? (int64_t)c->slicePairs[z + 1] - c->slicePairs[z] : 0;
+        if (covered) covered[z] = (c->prepared && (int)c->sliceStart.size() == NZ + 1) ? (int64_t)c->sliceStart[z + 1] - c->sliceStart[z] : 0;
+    }
+    if (samples) {
+        std::vector<unsigned long long> h((size_t)NZ, 0ull);
+        if (c->dSliceSamples.p) CUDA_TRY(c, cudaMemcpy(h.data(), c->dSliceSamples.p, sizeof(unsigned long long) * (size_t)NZ, cudaMemcpyDeviceToHost));
+        for (int z = 0; z < NZ; z++) samples[z] = (int64_t)h[z];
+    }
     return VPE_OK;
 }
 

@@ -176,7 +176,7 @@ class Engine:
         self._check(self.lib.vpe_set_march_options(self._ctx, C.byref(o)))
 
     def set_debug_options(self, march_kernel=0, no_skip=False, no_gray=False, no_row_pad=False, march_bands=0,
-                          march_tile_log2w=None, link_spin_ms=0, no_sweep_overlap=False):
+                          march_tile_log2w=None, link_spin_ms=0, sweep_overlap=False, no_tma_sweep=False, profile_slices=False):
         """VpeDebugOptions: experiment switches of the CUDA library (all defaults = production). march_kernel 1 = general
         kernel, 2 = round 1's per-fragment loop; no_gray / no_row_pad change the brick layout (fill again before marching)."""
         o = _abi.VpeDebugOptions()
@@ -184,8 +184,17 @@ class Engine:
         o.marchBands = int(march_bands)
         o.marchTileLog2W = 0 if march_tile_log2w is None else int(march_tile_log2w) + 1
         o.linkSpinMs = int(link_spin_ms)
-        o.noSweepOverlap = int(bool(no_sweep_overlap))
+        o.sweepOverlap = int(bool(sweep_overlap))
+        o.noTmaSweep = int(bool(no_tma_sweep))
+        o.profileSlices = int(bool(profile_slices))
         self._check(self.lib.vpe_set_debug_options(self._ctx, C.byref(o)))
+
+    def read_slice_profile(self):
+        """(pairs, covered metavoxels, ray samples) per light-axis slice of the last fill / march (needs profile_slices)."""
+        nz = self.grid[2]
+        out = [np.zeros(nz, dtype=np.int64) for _ in range(3)]
+        self._check(self.lib.vpe_read_slice_profile(self._ctx, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data))
+        return tuple(out)
 
     def composite_scene(self, particles_rgba, scene_rgba, target_format=0):
         """≙ Graphics.Blit(particlesRT, mainSceneRT, matBlendParticles) (VPR.cs:210). Returns the new scene."""

@@ -175,23 +175,32 @@ class SlabRenderer:
 
     def rebalance(self):
         """Move the slab boundaries so that the modelled frame time (balance_slabs) is minimal, from the
-        device times of the last profiled frame (self.profile = True during fill() and march()): each rank's
-        density and march-kernel time is spread evenly over its slices, which gives a per-slice cost profile
-        of the whole grid; all ranks compute the same partition from the same gathered numbers. The volume
-        must be filled again afterwards. Returns the new list of slabs."""
+        device times of the last profiled frame (self.profile = True during fill() and march()). A rank's density
+        and march-kernel time is spread over its slices in proportion to the work the engine counted per slice
+        ((particle, metavoxel) pairs of the fill, ray samples of the march; evenly where the engine has no such
+        profile), which gives a per-slice cost profile of the whole grid; all ranks compute the same partition
+        from the same gathered numbers. The volume must be filled again afterwards. Returns the new list of slabs."""
         e, d = self.e, self.dist
         if self.world == 1 or self._times is None:
             return [(self.z0, self.z1)]
         density_ms = e.elapsed_ms(self._times[0], self._times[1])
         march_ms = float(e.stats()["marchKernelMs"])
-        mine = (self.z0, self.z1, density_ms, march_ms)
+        nz = e.grid[2]
+        wd, wm = np.ones(nz), np.ones(nz)
+        prof = e.slice_profile() if hasattr(e, "slice_profile") else None
+        if prof is not None:
+            pairs, covered, samples = prof
+            # a covered metavoxel costs its voxels' loop overhead even with few particles: ~2 pairs' worth (measured shape)
+            wd = pairs.astype(np.float64) + 2.0 * covered.astype(np.float64) + 1e-9
+            wm = samples.astype(np.float64) + 1e-9
+        mine = (self.z0, self.z1, density_ms, march_ms, wd[self.z0:self.z1].tolist(), wm[self.z0:self.z1].tolist())
         rows = [None] * self.world
         d.all_gather_object(rows, mine)
-        nz = e.grid[2]
         dc, mc = np.zeros(nz), np.zeros(nz)
-        for (a, b, dm, mm) in rows:
-            dc[a:b] = dm / (b - a)
-            mc[a:b] = mm / (b - a)
+        for (a, b, dm, mm, w1, w2) in rows:
+            w1, w2 = np.asarray(w1), np.asarray(w2)
+            dc[a:b] = dm * w1 / w1.sum()
+            mc[a:b] = mm * w2 / w2.sum()
         # the sweep moves 16 bytes per voxel of a covered metavoxel; ~0.6 of the HBM rate measured alone
         gx, gy, _ = e.grid
         sweep = np.full(nz, gx * gy * float(e.N) ** 3 * 16.0 / 4.0e12 * 1e3)
@@ -445,6 +454,17 @@ class CudaSlabEngine:
 
     def stats(self):
         return self.eng.stats()
+
+    def profile_slices(self, on):
+        """Keep per-slice work figures of the fills and marches that follow (SlabRenderer.rebalance reads them).
+        self.debug holds the other VpeDebugOptions of this engine (set_debug_options replaces all of them)."""
+        self.eng.set_debug_options(profile_slices=bool(on), **getattr(self, "debug", {}))
+        self._profiling = bool(on)
+
+    def slice_profile(self):
+        if not getattr(self, "_profiling", False):
+            return None
+        return self.eng.read_slice_profile()
 
     def link_timeouts(self):
         """Waits of the sheet link and the image link that gave up (a peer that never arrived): must be 0."""
