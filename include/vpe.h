@@ -283,6 +283,11 @@ int vpe_read_particle_list(VpeContext* ctx, int x, int y, int z, int32_t* idx, i
 /* world-space centre of metavoxel (x,y,z) ≙ mvGrid[z,y,x].mPos, VPR.cs:390. */
 int vpe_read_metavoxel_position(VpeContext* ctx, int x, int y, int z, float pos[3]);
 
+/* q[i] = the fill kernel's inlined a[i] / b[i] (host arrays): the three divisions of the in-sphere body and 1/(1+density)
+ * use the fast path of div.rn.f32; the tests fuzz it against IEEE division over the operand ranges that occur.
+ * CUDA library only (the oracle divides). */
+int vpe_debug_div_rn(VpeContext* ctx, const float* a, const float* b, float* q, int n);
+
 int vpe_get_stats(VpeContext* ctx, VpeStats* stats);
 const char* vpe_last_error(VpeContext* ctx);
 int vpe_abi_version(void);

@@ -1038,6 +1038,11 @@ int vpe_read_light_depth_map(VpeContext* c, float* depth01) {
 
 // debug switches select kernels / layouts of the CUDA library; the oracle has one path and ignores them
 int vpe_set_debug_options(VpeContext* c, const VpeDebugOptions* o) { return (c && o) ? VPE_OK : VPE_E_INVALID_ARG; }
+int vpe_debug_div_rn(VpeContext* c, const float* a, const float* b, float* q, int n) {
+    if (!c || !a || !b || !q || n < 0) return VPE_E_INVALID_ARG;
+    for (int i = 0; i < n; i++) q[i] = a[i] / b[i];
+    return VPE_OK;
+}
 int vpe_read_slice_profile(VpeContext* c, int64_t*, int64_t*, int64_t*) { return fail(c, VPE_E_UNSUPPORTED, "slice profile: CUDA library only"); }
 
 int vpe_set_march_options(VpeContext* c, const VpeMarchOptions* o) {

@@ -1,4 +1,5 @@
-"""Time k_sweep_columns alone on one GPU: cfg3, whole grid as one slab, density pass then the sweep (16 B/voxel)."""
+"""Time the sweep kernel alone on one GPU: cfg3, whole grid as one slab, density pass then the sweep (16 B/voxel).
+usage: sweep_kernel_bench.py [cfg] [tma|reg]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -8,6 +9,8 @@ from vpe_b200 import scenes
 
 sc = scenes.make_scene(sys.argv[1] if len(sys.argv) > 1 else "cfg3")
 e = vpe_b200.engine_for_scene(None, sc)
+mode = sys.argv[2] if len(sys.argv) > 2 else "tma"
+e.set_debug_options(no_tma_sweep=(mode == "reg"))
 scenes.apply_scene(e, sc)
 gx, gy, gz = e.grid
 ts, td = [], []
@@ -20,4 +23,4 @@ for it in range(5):
     ts.append(st["fillKernelMs"])
 vox = st["voxelsFilled"]
 t = float(np.median(ts[1:]))
-print("density %.3f ms   sweep %.3f ms  %.0f GB/s (16 B/voxel, %d voxels)" % (float(np.median(td[1:])), t, vox * 16 / t / 1e6, vox))
+print(mode, "density %.3f ms   sweep %.3f ms  %.0f GB/s (16 B/voxel, %d voxels)" % (float(np.median(td[1:])), t, vox * 16 / t / 1e6, vox))

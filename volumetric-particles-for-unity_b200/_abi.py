@@ -120,6 +120,7 @@ PROTOTYPES = {
     "vpe_read_light_sheet": (C.c_int, [_P, _P]),
     "vpe_read_particle_list": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_int)]),
     "vpe_read_metavoxel_position": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "vpe_debug_div_rn": (C.c_int, [_P, _P, _P, _P, C.c_int]),
     "vpe_get_stats": (C.c_int, [_P, C.POINTER(VpeStats)]),
     "vpe_last_error": (C.c_char_p, [_P]),
     "vpe_abi_version": (C.c_int, []),

@@ -541,7 +541,7 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1, FillPhase ph
         }
         c->stats.fillLaunches++;
         if ((phase == FILL_FUSED || phase == FILL_DENSITY) && c->nCovered > 0) {  // the densities are final: derive the march's bitmap
-            k_occ_build<<<(x1 - x0) * (y1 - y0), 256, 0, c->stream>>>(g, c->dBrickOf.p, c->dNz.p, c->dOcc.p, c->occRowWords, x0, x1, y0);
+            k_occ_build<<<c->nCovered, 256, 0, c->stream>>>(g, c->dCovered.p, c->dTotals.p + 1, c->dNz.p, c->dOcc.p, c->occRowWords, x0, x1, y0, y1);
             c->stats.fillLaunches++;
         }
     }
@@ -1489,6 +1489,22 @@ int vpe_read_metavoxel_position(VpeContext* c, int x, int y, int z, float pos[3]
     if (x < 0 || y < 0 || z < 0 || x >= c->g.NX || y >= c->g.NY || z >= c->g.NZ) return fail(c, VPE_E_INVALID_ARG, "metavoxel index out of range");
     F3 p = mv_center(c->g, x, y, z);  // same routine the kernels call
     pos[0] = p.x; pos[1] = p.y; pos[2] = p.z;
+    return VPE_OK;
+}
+
+int vpe_debug_div_rn(VpeContext* c, const float* a, const float* b, float* q, int n) {
+    if (!c || !a || !b || !q || n < 0) return VPE_E_INVALID_ARG;
+    if (n == 0) return VPE_OK;
+    DeviceScope deviceScope(c->device);
+    DevBuf<float> da, db, dq;
+    CUDA_TRY(c, da.ensure(n)); CUDA_TRY(c, db.ensure(n)); CUDA_TRY(c, dq.ensure(n));
+    CUDA_TRY(c, cudaMemcpyAsync(da.p, a, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(db.p, b, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    k_debug_div<<<div_up(n, 256), 256, 0, c->stream>>>(da.p, db.p, dq.p, n);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(q, dq.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    da.release(); db.release(); dq.release();
     return VPE_OK;
 }
 

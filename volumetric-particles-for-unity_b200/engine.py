@@ -189,6 +189,14 @@ class Engine:
         o.profileSlices = int(bool(profile_slices))
         self._check(self.lib.vpe_set_debug_options(self._ctx, C.byref(o)))
 
+    def debug_div_rn(self, a, b):
+        """The fill kernel's inlined division, elementwise (test hook)."""
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        q = np.empty_like(a)
+        self._check(self.lib.vpe_debug_div_rn(self._ctx, a.ctypes.data, b.ctypes.data, q.ctypes.data, a.size))
+        return q
+
     def read_slice_profile(self):
         """(pairs, covered metavoxels, ray samples) per light-axis slice of the last fill / march (needs profile_slices)."""
         nz = self.grid[2]
