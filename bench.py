@@ -662,7 +662,10 @@ def run_cuda_slabs(args):
         "roofline_fill": {"kernel": "k_fill_columns<density> + k_sweep_tma", "bound": "hbm", "achieved": fill_bytes / (fill_ms * 1e-3) / 1e9,
                           "peak": peak * world, "unit": "GB/s", "frac": fill_bytes / (fill_ms * 1e-3) / 1e9 / (peak * world),
                           "traffic": recorded_traffic("k_fill_columns"), "algorithmic_bytes": fill_bytes, "ms": fill_ms,
-                          "bytes_per_voxel": 8.0 + 8.0 / N, "note": "whole fill step (bin + density + sweep), slowest rank"},
+                          "bytes_per_voxel": 8.0 + 8.0 / N, "traffic_sweep": recorded_traffic("k_sweep_tma"),
+                          "note": "whole fill step (bin + density + sweep), slowest rank; algorithmic bytes are the fused single-GPU "
+                                  "figure (8 B/voxel written once); the split really moves 8 (density, written) + 16 (sweep, in place) "
+                                  "B/voxel; traffic = the single-GPU ncu capture of the fused kernel, traffic_sweep = of k_sweep_tma over the whole grid"},
         "cpu_baseline": cpu,
         "parity": {"link_timeouts": timeouts, "vs_single_gpu": single, "vs_oracle": parity},
     }

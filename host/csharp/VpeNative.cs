@@ -62,6 +62,15 @@ namespace MetavoxelEngine.Native
         public float fillMs, marchMs;
         public long brickPoolBytes;
         public float fillKernelMs, marchKernelMs;
+        public long raySamplesSkipped;     // of raySamples: samples in empty space the march does not fetch
+    }
+
+    /// VpeDebugOptions of include/vpe.h: experiment / measurement switches, all zero = production behaviour.
+    [StructLayout(LayoutKind.Sequential)]
+    public struct VpeDebugOptions
+    {
+        public int marchKernel, noSkip, noGray, noRowPad, marchBands, marchTileLog2W, linkSpinMs, sweepOverlap, noTmaSweep, profileSlices;
+        public int reserved0, reserved1, reserved2, reserved3, reserved4, reserved5;
     }
 
     /// VpeMarchOptions of include/vpe.h: UNORM8 target (particlesRT is ARGB32, VPR.cs:228), the debug views of
@@ -92,6 +101,7 @@ namespace MetavoxelEngine.Native
         [DllImport(Lib)] public static extern int vpe_set_march_options(IntPtr ctx, ref VpeMarchOptions options);
         [DllImport(Lib)] public static extern int vpe_composite_scene(IntPtr ctx, [In] float[] particlesRgba, [In, Out] float[] sceneRgba, int numPixels, int targetFormat);
         [DllImport(Lib)] public static extern int vpe_get_stats(IntPtr ctx, out VpeStats stats);
+        [DllImport(Lib)] public static extern int vpe_set_debug_options(IntPtr ctx, ref VpeDebugOptions options);
         [DllImport(Lib)] public static extern IntPtr vpe_last_error(IntPtr ctx);
         [DllImport(Lib)] public static extern int vpe_abi_version();
 

@@ -51,7 +51,8 @@ def test_struct_layout_matches_the_c_header(tmp_path):
               "VpeParticle": [f for f, _ in _abi.VpeParticle._fields_],
               "VpeCamera": [f for f, _ in _abi.VpeCamera._fields_],
               "VpeStats": [f for f, _ in _abi.VpeStats._fields_],
-              "VpeMarchOptions": [f for f, _ in _abi.VpeMarchOptions._fields_]}
+              "VpeMarchOptions": [f for f, _ in _abi.VpeMarchOptions._fields_],
+              "VpeDebugOptions": [f for f, _ in _abi.VpeDebugOptions._fields_]}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vpe.h"', "int main(void){"]
     for s, fs in fields.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (s, s))
@@ -69,6 +70,28 @@ def test_struct_layout_matches_the_c_header(tmp_path):
         for f in fs:
             assert int(got["%s.%s" % (s, f)]) == getattr(ct, f).offset, "%s.%s" % (s, f)
     assert C.sizeof(_abi.VpeParticle) == 28  # ParticleSystem.Particle fields read by VPR.cs:418,425,583-586
+
+
+def test_csharp_structs_have_the_size_of_the_c_structs():
+    """host/csharp/VpeNative.cs cannot be compiled here; at least its LayoutKind.Sequential structs must add up to the C
+    structs' sizes (natural alignment), and every P/Invoke must name a function the header declares. A struct that lags
+    behind the header (a field added in C only) would let vpe_get_stats write past the managed struct."""
+    src = open(os.path.join(ROOT, "host", "csharp", "VpeNative.cs")).read()
+    src = re.sub(r"//[^\n]*", "", src)
+    prim = {"int": (4, 4), "float": (4, 4), "long": (8, 8), "IntPtr": (8, 8)}
+    layouts = {}
+    for name, body in re.findall(r"public struct (\w+)\s*\{(.*?)\}", src, flags=re.S):
+        off, align = 0, 1
+        for typ, names in re.findall(r"public\s+(\w+)\s+([^;]+);", body):
+            size, al = prim[typ] if typ in prim else layouts[typ]
+            for _ in names.split(","):
+                off = -(-off // al) * al + size
+                align = max(align, al)
+        layouts[name] = (-(-off // align) * align, align)
+    for name in ("VpeTransform", "VpeConfig", "VpeParticle", "VpeCamera", "VpeStats", "VpeMarchOptions", "VpeDebugOptions"):
+        assert layouts[name][0] == C.sizeof(getattr(_abi, name)), name
+    externs = re.findall(r"extern\s+\w+\s+(vpe_\w+)\s*\(", src)
+    assert externs and set(externs) <= set(declared_functions())
 
 
 def test_product_fails_loudly_without_a_gpu():

@@ -209,6 +209,14 @@ class SlabRenderer:
         self._times = None
         return slabs_
 
+    def check_links(self):
+        """Raises when a bounded wait of the sheet link or the image link gave up (a peer that never signalled): the
+        frame just rendered is then not the reference's image.  Synchronises this rank's stream."""
+        if self.world > 1 and hasattr(self.e, "link_timeouts"):
+            n = self.e.link_timeouts()
+            if n:
+                raise RuntimeError("rank %d: %d sheet/image link waits gave up; the frame is not valid" % (self.rank, n))
+
     # -- march ------------------------------------------------------------------------------------
     def march(self, camera, gather=True, count_samples=True, host_image=None):
         """Returns (rgba, total_ray_samples): rgba is the full H x W x 4 image on rank 0 when
@@ -241,6 +249,8 @@ class SlabRenderer:
                 parts += [recv_over[s], recv_under[s]]
             band = e.composite(parts, per * w).reshape(per, w, 4)
         total = e.all_reduce_sum(d, samples) if count_samples else None
+        if count_samples:
+            self.check_links()                       # the host has synchronised for the counter anyway
         if host_image is not None:
             e.copy_band_to_host(band, host_image.band())
             return None, total
