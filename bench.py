@@ -511,7 +511,8 @@ def run_cuda_slabs(args):
     eng = CudaSlabEngine(sc, rank, world, local_rank)
     eng.debug = dict(sweep_overlap=bool(args.sweep_overlap))
     eng.profile_slices(False)   # pushes eng.debug to the library
-    r = SlabRenderer(eng, dist, fill_bands=args.fill_bands if getattr(args, "fill_bands", 0) else None)
+    r = SlabRenderer(eng, dist, fill_bands=args.fill_bands if getattr(args, "fill_bands", 0) else None,
+                     head_fused=not args.no_head_fused and not args.sweep_overlap)
     cam = sc["camera"]
     W, H = cam["width"], cam["height"]
     n = sc["particles"].shape[0]
@@ -640,7 +641,8 @@ def run_cuda_slabs(args):
         "config": {"workload": workload_name(cfg_name, sc),
             "parallelism": "light-axis slabs x%d (fill: %s; march: slab-local, %s, ordered compositing by screen band)" % (
                 world, ("persistent TMA sweep kernel concurrent with the density pass, sheet handed to the next rank over NVLink peer memory"
-                        if args.sweep_overlap else "TMA sweep kernel after the density pass, sheet handed to the next rank over NVLink peer memory")
+                        if args.sweep_overlap else "TMA sweep kernel after the density pass, sheet handed to the next rank over NVLink peer memory"
+                        + ("; the rank nearest the light runs the fused fill kernel and feeds the link itself" if r.head_fused else ""))
                 if r.linked else "sheet rows over NCCL send/recv in %d bands" % len(r.bands),
                 "non-zero partials stored into the compositing rank's memory by the march kernel (peer memory + flags)"
                 if r._image_links.get((W, H)) else "NCCL all-to-all of the partial images"),
@@ -689,6 +691,7 @@ def main():
     ap.add_argument("--no-skip", action="store_true", help="experiments: sample every step (ignore the empty-space bitmap)")
     ap.add_argument("--no-rebalance", action="store_true", help="N>1: keep equal slabs (default: balance the slab boundaries during warm-up)")
     ap.add_argument("--sweep-overlap", action="store_true", help="N>1 experiments: linked sweep concurrently with the density pass instead of after it")
+    ap.add_argument("--no-head-fused", action="store_true", help="N>1 experiments: the rank nearest the light splits its fill (density + linked sweep) like the others")
     ap.add_argument("--fill-bands", type=int, default=0, help="N>1: row bands of the NCCL fill pipeline (default: the peer-memory sheet link)")
     args = ap.parse_args()
     if args.check_image:

@@ -70,7 +70,8 @@ namespace MetavoxelEngine.Native
     public struct VpeDebugOptions
     {
         public int marchKernel, noSkip, noGray, noRowPad, marchBands, marchTileLog2W, linkSpinMs, sweepOverlap, noTmaSweep, profileSlices;
-        public int reserved0, reserved1, reserved2, reserved3, reserved4, reserved5;
+        public int noHeadFused;
+        public int reserved0, reserved1, reserved2, reserved3, reserved4;
     }
 
     /// VpeMarchOptions of include/vpe.h: UNORM8 target (particlesRT is ARGB32, VPR.cs:228), the debug views of

@@ -214,6 +214,11 @@ float* vpe_light_sheet_device(VpeContext* ctx);
 int vpe_sheet_link_create(VpeContext* ctx, void* ipcHandle64, void** devPtr);
 int vpe_sheet_link_connect(VpeContext* ctx, const void* upstream, const void* downstream, int handlesAreIpc);
 int vpe_fill_sweep_linked(VpeContext* ctx);
+/* The whole linked fill of this rank after vpe_fill_prepare, in the cheapest form its place in the chain allows: the rank
+ * with no upstream neighbour (the slab nearest the light, VPR.cs:505 starts there) has nothing to wait for and runs the
+ * FUSED kernel of vpe_fill, which stores its exit values into the downstream inbox itself; every other rank runs
+ * vpe_fill_density + vpe_fill_sweep_linked. All ranks call it once per fill. Same bits as every other path. */
+int vpe_fill_linked(VpeContext* ctx);
 int vpe_sheet_link_status(VpeContext* ctx, int* timeouts);
 /* Slab-local march: two premultiplied RGBA partial images (device, height*width*4 floats each):
  * over = the slab's slices <= zBoundary composited back-to-front (phase 1, VPR.cs:652-681),
@@ -256,7 +261,8 @@ typedef struct VpeDebugOptions {
                                is issue-bound and loses more than the sweep gains at 8 GPUs, so this is off by default    */
     int32_t noTmaSweep;     /* 1 = register-staged sweep kernels (k_sweep_columns / k_sweep_overlapped) instead of the TMA pipeline  */
     int32_t profileSlices;  /* 1 = keep per-slice work figures of the fills and marches that follow (vpe_read_slice_profile)        */
-    int32_t reserved[6];
+    int32_t noHeadFused;    /* 1 = vpe_fill_linked splits the fill (density + linked sweep) on the head rank too, as round 1 did     */
+    int32_t reserved[5];
 } VpeDebugOptions;
 int vpe_set_debug_options(VpeContext* ctx, const VpeDebugOptions* options);
 /* Work per light-axis slice of the last fill / march of this context (NZ entries each, NULL = not wanted; slices outside the

@@ -131,6 +131,60 @@ def test_linked_sweep_two_contexts_on_one_gpu():
     check_volume()
 
 
+@pytest.mark.parametrize("n_vox", [32, 12])
+def test_head_rank_runs_the_fused_kernel_and_feeds_the_link(n_vox):
+    """vpe_fill_linked: the rank nearest the light has nothing upstream, so it does not split its fill - the fused
+    kernel (k_fill_columns<false, ., HEAD>) stores its exit sheet into the next rank's inbox and raises the flags the
+    linked sweep would; the other ranks run density + linked sweep. Three contexts of one process, three frames
+    (epochs, acknowledge flags): volume, final sheet and the image are those of the single-context fill; the switch
+    noHeadFused gives the same bits through the split path."""
+    import torch
+    sc = _scene()
+    sc["numVoxels"] = n_vox
+    cam = sc["camera"]
+    h, w = cam["height"], cam["width"]
+    one = vpe_b200.engine_for_scene(None, sc)
+    scenes.apply_scene(one, sc)
+    one.fill(sc["particles"], sc["emitter"])
+    img_one, smp_one = one.march(cam)
+    ranks = [slabs.CudaSlabEngine(sc, r, 3, 0) for r in range(3)]
+    ptrs = [e.eng.sheet_link_create()[1] for e in ranks]
+    for r, e in enumerate(ranks):
+        e.eng.sheet_link_connect(ptrs[r - 1] if r > 0 else None, ptrs[r + 1] if r < 2 else None)
+    gx, gy, gz = ranks[0].grid
+    for it in range(4):
+        if it == 3:
+            ranks[0].eng.set_debug_options(no_head_fused=True)
+        for e in ranks:
+            e.fill_prepare(sc["particles"], sc["emitter"])
+        for e in ranks:  # upstream first (one GPU)
+            e.fill_linked()
+        torch.cuda.synchronize()
+        st = ranks[0].eng.stats()
+        assert st["fillLaunches"] >= 1
+        assert all(e.eng.sheet_link_timeouts() == 0 for e in ranks), ranks[0].eng.lib.vpe_last_error(ranks[0].eng._ctx)
+        assert np.array_equal(ranks[2].eng.read_light_sheet(), one.read_light_sheet())
+        cov = 0
+        for z in range(gz):
+            owner = [e for e in ranks if e.slab[0] <= z < e.slab[1]][0]
+            for y in range(gy):
+                for x in range(gx):
+                    a, b = one.read_brick(x, y, z), owner.eng.read_brick(x, y, z)
+                    assert (a is None) == (b is None)
+                    if a is not None:
+                        cov += 1
+                        assert np.array_equal(a, b)
+        assert cov == one.stats()["numMetavoxelsCovered"]
+        parts, total = [], 0
+        for e in ranks:  # the head's empty-space bitmap comes from the fused kernel
+            over, under = e.march_partial(cam)
+            parts += [over, under]
+            total += e.last_ray_samples()
+        out = ranks[0].composite([p.clone() for p in parts], h * w).reshape(h, w, 4).cpu().numpy()
+        assert total == int(smp_one.sum())
+        assert max_rel_err(out, img_one) <= 1e-5
+
+
 @pytest.mark.parametrize("n_vox,grid,ranks_z", [(64, (2, 2, 4), [(0, 1), (1, 4)]), (12, (3, 3, 5), [(0, 2), (2, 3), (3, 5)]),
                                                (32, (2, 3, 3), [(0, 1), (1, 2), (2, 3)])])
 def test_linked_sweep_other_brick_sizes_and_three_slabs(n_vox, grid, ranks_z):

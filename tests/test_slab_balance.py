@@ -7,24 +7,24 @@ import numpy as np
 from vpe_b200 import slabs
 
 
-def frame_time(cuts, dc, sc, mc, prepare=0.1, lag=0.07):
+def frame_time(cuts, dc, sc, mc, prepare=0.1, lag=0.07, head=1.0):
     """The model of balance_slabs, evaluated for one partition (cuts = [(z0, z1), ...])."""
     sweep_prev, worst = -1e30, 0.0
-    for (a, b) in cuts:
+    for i, (a, b) in enumerate(cuts):
         d = prepare + float(np.sum(dc[a:b]))
-        se = max(d + float(np.sum(sc[a:b])), sweep_prev + lag)
+        se = max(d + float(np.sum(sc[a:b])) * (head if i == 0 else 1.0), sweep_prev + lag)
         worst = max(worst, se + float(np.sum(mc[a:b])))
         sweep_prev = se
     return worst
 
 
-def brute_force(dc, sc, mc, world):
+def brute_force(dc, sc, mc, world, head=1.0):
     nz = len(dc)
     best = None
     for inner in itertools.combinations(range(1, nz), world - 1):
         edges = (0,) + inner + (nz,)
         cuts = [(edges[i], edges[i + 1]) for i in range(world)]
-        t = frame_time(cuts, dc, sc, mc)
+        t = frame_time(cuts, dc, sc, mc, head=head)
         if best is None or t < best[0] - 1e-12:
             best = (t, cuts)
     return best
@@ -71,3 +71,16 @@ def test_march_heavy_slices_near_the_camera_get_thinner_slabs():
 def test_one_rank_and_as_many_ranks_as_slices():
     assert slabs.balance_slabs(np.ones(5), np.ones(5), np.ones(5), 1)[0] == [(0, 5)]
     assert slabs.balance_slabs(np.ones(5), np.ones(5), np.ones(5), 5)[0] == [(i, i + 1) for i in range(5)]
+
+
+def test_head_rank_with_the_fused_kernel_takes_more_slices():
+    """The rank nearest the light runs the fused fill kernel (its sweep costs a fraction of a separate sweep kernel):
+    the model scales slab 0's sweep cost; exact against exhaustive search, and slab 0 never gets thinner."""
+    rng = np.random.default_rng(3)
+    for trial in range(4):
+        nz, world = 10, int(rng.integers(2, 4))
+        dc, sc, mc = rng.uniform(0.2, 1, nz), rng.uniform(0.2, 0.5, nz), rng.uniform(0, 0.5, nz)
+        cuts, t = slabs.balance_slabs(dc, sc, mc, world, head_sweep_factor=0.35)
+        t_best, _ = brute_force(dc, sc, mc, world, head=0.35)
+        assert abs(t - t_best) < 1e-9
+        assert t <= slabs.balance_slabs(dc, sc, mc, world)[1] + 1e-12

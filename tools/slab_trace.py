@@ -13,10 +13,10 @@ rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 sc = scenes.make_scene(sys.argv[1] if len(sys.argv) > 1 else "cfg3")
-mode = sys.argv[2] if len(sys.argv) > 2 else "nooverlap"      # overlap | nooverlap | regsweep
+mode = sys.argv[2] if len(sys.argv) > 2 else "nooverlap"      # overlap | nooverlap | regsweep | split (= nooverlap, head rank splits its fill too)
 eng = slabs.CudaSlabEngine(sc, rank, world, lr)
 eng.debug = dict(sweep_overlap=(mode == "overlap"), no_tma_sweep=(mode == "regsweep"))
-r = slabs.SlabRenderer(eng, dist)
+r = slabs.SlabRenderer(eng, dist, head_fused=(mode in ("nooverlap", "regsweep")))
 cam = sc["camera"]
 parts = torch.from_numpy(sc["particles"]).cuda()
 eng.profile_slices(True)
@@ -40,8 +40,11 @@ for rep in range(2):
     h0 = time.perf_counter()
     mark("start")
     e.fill_prepare(parts, sc["emitter"]); mark("prepare")
-    e.fill_density(); mark("density")
-    e.fill_sweep_linked(); mark("sweep")
+    if r.head_fused:
+        mark("density"); e.fill_linked(); mark("sweep")      # head rank: ONE fused kernel
+    else:
+        e.fill_density(); mark("density")
+        e.fill_sweep_linked(); mark("sweep")
     e.march_linked(cam); mark("march")
     e.composite_linked(per, w); mark("composite")
     torch.cuda.synchronize()

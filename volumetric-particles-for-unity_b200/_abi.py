@@ -71,7 +71,7 @@ class VpeMarchOptions(C.Structure):
 class VpeDebugOptions(C.Structure):
     _fields_ = [("marchKernel", C.c_int32), ("noSkip", C.c_int32), ("noGray", C.c_int32), ("noRowPad", C.c_int32),
                 ("marchBands", C.c_int32), ("marchTileLog2W", C.c_int32), ("linkSpinMs", C.c_int32),
-                ("sweepOverlap", C.c_int32), ("noTmaSweep", C.c_int32), ("profileSlices", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("sweepOverlap", C.c_int32), ("noTmaSweep", C.c_int32), ("profileSlices", C.c_int32), ("noHeadFused", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 assert C.sizeof(VpeParticle) == 28
@@ -107,6 +107,7 @@ PROTOTYPES = {
     "vpe_sheet_link_create": (C.c_int, [_P, _P, C.POINTER(_P)]),
     "vpe_sheet_link_connect": (C.c_int, [_P, _P, _P, C.c_int]),
     "vpe_fill_sweep_linked": (C.c_int, [_P]),
+    "vpe_fill_linked": (C.c_int, [_P]),
     "vpe_sheet_link_status": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "vpe_march_partial_device": (C.c_int, [_P, C.POINTER(VpeCamera), _P, _P, _P]),
     "vpe_image_link_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.POINTER(_P)]),

@@ -298,6 +298,7 @@ void preload_kernels(int device) {
     preload(k_particle_setup); preload(k_scatter_pairs); preload(k_sort_lists); preload(k_scan_reduce); preload(k_scan_blocks);
     preload(k_scan_final); preload(k_fill_value); preload(k_occ_build); preload(k_mv_camera); preload(k_popcount);
     preload(k_fill_columns<false, false>); preload(k_fill_columns<false, true>); preload(k_fill_columns<true, false>);
+    preload(k_fill_columns<false, false, true>); preload(k_fill_columns<false, true, true>);
     preload(k_sweep_columns<false, false>); preload(k_sweep_columns<true, false>); preload(k_sweep_columns<false, true>);
     preload(k_sweep_columns<true, true>); preload(k_sweep_overlapped<false>); preload(k_sweep_overlapped<true>);
     preload_march<0>(); preload_march<32>(); preload_march<64>();
@@ -305,6 +306,7 @@ void preload_kernels(int device) {
     preload(k_image_signal); preload(k_composite_linked); preload(k_composite); preload(k_raster_depth);
     preload(k_composite_scene); preload(k_order_index);
     prefer_max_shared(k_fill_columns<false, false>); prefer_max_shared(k_fill_columns<false, true>); prefer_max_shared(k_fill_columns<true, false>);
+    prefer_max_shared(k_fill_columns<false, false, true>); prefer_max_shared(k_fill_columns<false, true, true>);
     prefer_max_shared(k_sweep_columns<false, true>); prefer_max_shared(k_sweep_columns<true, true>);
     prefer_max_shared(k_sweep_overlapped<false>); prefer_max_shared(k_sweep_overlapped<true>);
     prefer_max_shared(k_composite_linked); prefer_max_shared(k_occ_build);
@@ -405,7 +407,7 @@ int fill_prepare_impl(VpeContext* c, const float* particlesDev, int n, const Vpe
     return VPE_OK;
 }
 
-enum FillPhase { FILL_FUSED, FILL_DENSITY, FILL_SWEEP, FILL_SWEEP_LINKED };
+enum FillPhase { FILL_FUSED, FILL_DENSITY, FILL_SWEEP, FILL_SWEEP_LINKED, FILL_FUSED_HEAD };
 
 // cuTensorMapEncodeTiled through the runtime (no link against libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -492,32 +494,36 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1, FillPhase ph
     }
     CUDA_TRY(c, cudaEventRecord(c->evFillK0, c->stream));
     if (phase != FILL_DENSITY) c->bricksGray = g.gray != 0;
-    if (c->nCovered > 0 || phase == FILL_SWEEP_LINKED) {  // a linked sweep always runs: its flags must flow
+    if (c->nCovered > 0 || phase == FILL_SWEEP_LINKED || phase == FILL_FUSED_HEAD) {  // a linked fill always runs: its flags must flow
         // one launch: every voxel column of the region walks all slices of the slab
         const int warpTiles = ((g.N + 7) / 8) * ((g.N + 3) / 4);
         const dim3 grid((x1 - x0) * (y1 - y0), div_up(warpTiles, FILLC_THREADS / 32));
-        if (phase == FILL_FUSED && g.gray) k_fill_columns<false, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p);
-        else if (phase == FILL_FUSED) k_fill_columns<false, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p);
-        else if (phase == FILL_DENSITY) k_fill_columns<true, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p);
+        SheetLink link;
+        memset(&link, 0, sizeof(link));
+        if (phase == FILL_SWEEP_LINKED || phase == FILL_FUSED_HEAD) {
+            const LinkLayout l = link_layout(g);
+            char* own = static_cast<char*>(c->linkOwn);
+            link.inbox = reinterpret_cast<const float*>(own);
+            link.flagIn = reinterpret_cast<const unsigned*>(own + l.flagOff);
+            link.ackIn = reinterpret_cast<const unsigned*>(own + l.ackOff);
+            link.timeouts = reinterpret_cast<unsigned*>(own + l.timeoutOff);
+            link.hasUp = c->linkUp != nullptr;
+            link.hasDown = c->linkDown != nullptr;
+            if (link.hasUp) link.upAck = reinterpret_cast<unsigned*>(static_cast<char*>(c->linkUp) + l.ackOff);
+            if (link.hasDown) {
+                link.downInbox = reinterpret_cast<float*>(c->linkDown);
+                link.downFlag = reinterpret_cast<unsigned*>(static_cast<char*>(c->linkDown) + l.flagOff);
+            }
+            link.epoch = ++c->linkEpoch;
+            link.spinLimit = (long long)(c->dbg.linkSpinMs > 0 ? c->dbg.linkSpinMs : 2000) * 2000000ll;  // ~2 GHz ticks
+        }
+        if (phase == FILL_FUSED && g.gray) k_fill_columns<false, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p, link);
+        else if (phase == FILL_FUSED) k_fill_columns<false, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p, link);
+        else if (phase == FILL_FUSED_HEAD && g.gray) k_fill_columns<false, true, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p, link);
+        else if (phase == FILL_FUSED_HEAD) k_fill_columns<false, false, true><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p, link);
+        else if (phase == FILL_DENSITY) k_fill_columns<true, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, c->dCubeFp.p, link);
         else {
-            SheetLink link;
-            memset(&link, 0, sizeof(link));
             if (phase == FILL_SWEEP_LINKED) {
-                const LinkLayout l = link_layout(g);
-                char* own = static_cast<char*>(c->linkOwn);
-                link.inbox = reinterpret_cast<const float*>(own);
-                link.flagIn = reinterpret_cast<const unsigned*>(own + l.flagOff);
-                link.ackIn = reinterpret_cast<const unsigned*>(own + l.ackOff);
-                link.timeouts = reinterpret_cast<unsigned*>(own + l.timeoutOff);
-                link.hasUp = c->linkUp != nullptr;
-                link.hasDown = c->linkDown != nullptr;
-                if (link.hasUp) link.upAck = reinterpret_cast<unsigned*>(static_cast<char*>(c->linkUp) + l.ackOff);
-                if (link.hasDown) {
-                    link.downInbox = reinterpret_cast<float*>(c->linkDown);
-                    link.downFlag = reinterpret_cast<unsigned*>(static_cast<char*>(c->linkDown) + l.flagOff);
-                }
-                link.epoch = ++c->linkEpoch;
-                link.spinLimit = (long long)(c->dbg.linkSpinMs > 0 ? c->dbg.linkSpinMs : 2000) * 2000000ll;  // ~2 GHz ticks
                 const bool tma = c->brickMapOk && !c->dbg.noTmaSweep;
                 if (c->densitySignalled) {
                     // persistent kernel on its own stream, concurrent with the density pass launched just before
@@ -540,7 +546,7 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1, FillPhase ph
             else k_sweep_columns<false, false><<<grid, FILLC_THREADS, 0, c->stream>>>(g, a, c->dBrickOf.p, link);
         }
         c->stats.fillLaunches++;
-        if ((phase == FILL_FUSED || phase == FILL_DENSITY) && c->nCovered > 0) {  // the densities are final: derive the march's bitmap
+        if ((phase == FILL_FUSED || phase == FILL_FUSED_HEAD || phase == FILL_DENSITY) && c->nCovered > 0) {  // the densities are final: derive the march's bitmap
             k_occ_build<<<c->nCovered, 256, 0, c->stream>>>(g, c->dCovered.p, c->dTotals.p + 1, c->dNz.p, c->dOcc.p, c->occRowWords, x0, x1, y0, y1);
             c->stats.fillLaunches++;
         }
@@ -1207,6 +1213,18 @@ int vpe_fill_sweep_linked(VpeContext* c) {
     if (!c->prepared) return fail(c, VPE_E_NOT_READY, "vpe_fill_prepare has not been called");
     if (!c->linkOwn) return fail(c, VPE_E_NOT_READY, "vpe_sheet_link_create has not been called");
     DeviceScope deviceScope(c->device);
+    return fill_region_impl(c, 0, c->g.NX, 0, c->g.NY, FILL_SWEEP_LINKED);
+}
+
+int vpe_fill_linked(VpeContext* c) {
+    if (!c) return VPE_E_INVALID_ARG;
+    if (!c->prepared) return fail(c, VPE_E_NOT_READY, "vpe_fill_prepare has not been called");
+    if (!c->linkOwn) return fail(c, VPE_E_NOT_READY, "vpe_sheet_link_create has not been called");
+    DeviceScope deviceScope(c->device);
+    if (!c->linkUp && c->linkDown && !c->dbg.noHeadFused)  // head of the chain: nothing to wait for, no reason to split
+        return fill_region_impl(c, 0, c->g.NX, 0, c->g.NY, FILL_FUSED_HEAD);
+    const int rc = fill_region_impl(c, 0, c->g.NX, 0, c->g.NY, FILL_DENSITY);
+    if (rc) return rc;
     return fill_region_impl(c, 0, c->g.NX, 0, c->g.NY, FILL_SWEEP_LINKED);
 }
 

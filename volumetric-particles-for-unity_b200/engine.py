@@ -176,7 +176,8 @@ class Engine:
         self._check(self.lib.vpe_set_march_options(self._ctx, C.byref(o)))
 
     def set_debug_options(self, march_kernel=0, no_skip=False, no_gray=False, no_row_pad=False, march_bands=0,
-                          march_tile_log2w=None, link_spin_ms=0, sweep_overlap=False, no_tma_sweep=False, profile_slices=False):
+                          march_tile_log2w=None, link_spin_ms=0, sweep_overlap=False, no_tma_sweep=False, profile_slices=False,
+                          no_head_fused=False):
         """VpeDebugOptions: experiment switches of the CUDA library (all defaults = production). march_kernel 1 = general
         kernel, 2 = round 1's per-fragment loop; no_gray / no_row_pad change the brick layout (fill again before marching)."""
         o = _abi.VpeDebugOptions()
@@ -187,6 +188,7 @@ class Engine:
         o.sweepOverlap = int(bool(sweep_overlap))
         o.noTmaSweep = int(bool(no_tma_sweep))
         o.profileSlices = int(bool(profile_slices))
+        o.noHeadFused = int(bool(no_head_fused))
         self._check(self.lib.vpe_set_debug_options(self._ctx, C.byref(o)))
 
     def debug_div_rn(self, a, b):
@@ -259,6 +261,10 @@ class Engine:
 
     def fill_sweep_linked(self):
         self._check(self.lib.vpe_fill_sweep_linked(self._ctx))
+
+    def fill_linked(self):
+        """The linked fill after fill_prepare: fused kernel on the head rank, density + linked sweep elsewhere."""
+        self._check(self.lib.vpe_fill_linked(self._ctx))
 
     def sheet_link_timeouts(self):
         n = C.c_int(0)

@@ -50,7 +50,12 @@ def image_band(height, world, rank):
     return min(rank * per, height), min((rank + 1) * per, height)
 
 
-def balance_slabs(density_cost, sweep_cost, march_cost, world, prepare=0.1, lag=0.07):
+# Cost of the sweep inside the fused fill kernel relative to the sweep as a kernel of its own (cfg3, one B200: fused 10.3 ms,
+# density pass 9.2 ms, sweep alone 3.1 ms): what the rank at the head of the chain pays for its sweep (profiles/r02_scaling.md).
+HEAD_FUSED_SWEEP_FACTOR = 0.35
+
+
+def balance_slabs(density_cost, sweep_cost, march_cost, world, prepare=0.1, lag=0.07, head_sweep_factor=1.0):
     """Contiguous light-axis slabs [z0, z1) per rank that minimise the modelled frame time.
 
     Per-slice costs (ms): density_cost = the particle loop, sweep_cost = the light sweep, march_cost = the
@@ -58,7 +63,8 @@ def balance_slabs(density_cost, sweep_cost, march_cost, world, prepare=0.1, lag=
         density ends   d_r = prepare + sum(density_cost[a:b])
         sweep ends     s_r = max(d_r + sum(sweep_cost[a:b]), s_{r-1} + lag)     (the sheet chain)
         march ends     e_r = s_r + sum(march_cost[a:b])
-    and the frame ends at max_r e_r (the compositing exchange waits for every rank). The sweep of a rank
+    and the frame ends at max_r e_r (the compositing exchange waits for every rank). head_sweep_factor scales the sweep
+    cost of rank 0, which may run the fused kernel (HEAD_FUSED_SWEEP_FACTOR) instead of density + sweep. The sweep of a rank
     cannot end before that of the rank nearer the light, so ranks late in the chain should carry less
     march work; exact search by dynamic programming over (rank, first slice) with Pareto-pruned states."""
     nz = len(density_cost)
@@ -78,6 +84,8 @@ def balance_slabs(density_cost, sweep_cost, march_cost, world, prepare=0.1, lag=
             for b in ends:
                 d = prepare + cd[b] - cd[a]
                 sw, ma = cs[b] - cs[a], cm[b] - cm[a]
+                if r == 0:
+                    sw *= head_sweep_factor
                 for (sp, worst, cuts) in lst:
                     se = max(d + sw, sp + lag)
                     cand = (se, max(worst, se + ma), cuts + (b,))
@@ -108,7 +116,7 @@ class SlabRenderer:
     """fill() + march() of one rank.  `engine` is a slab engine adapter, `dist` is torch.distributed
     (already initialised) or None for a single process."""
 
-    def __init__(self, engine, dist=None, fill_bands=None, image_link=True):
+    def __init__(self, engine, dist=None, fill_bands=None, image_link=True, head_fused=True):
         self.e = engine
         self.dist = dist
         self.rank = dist.get_rank() if dist is not None else 0
@@ -128,6 +136,8 @@ class SlabRenderer:
         self.linked = False
         if self.world > 1 and fill_bands is None and hasattr(engine, "link_neighbours"):
             self.linked = bool(engine.link_neighbours(dist, self.rank, self.world))
+        # the head of the chain does not split its fill (engines that can: vpe_fill_linked)
+        self.head_fused = bool(self.linked and self.rank == 0 and head_fused and hasattr(engine, "fill_linked"))
 
     # -- fill -------------------------------------------------------------------------------------
     def fill(self, particles, emitter):
@@ -139,6 +149,12 @@ class SlabRenderer:
             e.fill_region(0, gx, 0, gy)             # fused: nothing to wait for
             return
         t0 = e.record_event() if self.profile else None
+        if self.head_fused:
+            # nothing upstream of the slab nearest the light: the fused kernel runs and feeds the sheet link itself
+            e.fill_linked()
+            if self.profile:
+                self._times = [t0, e.record_event()]
+            return
         e.fill_density()                            # phase 1: the particle loop of the whole slab, no dependency
         t1 = e.record_event() if self.profile else None
         if self.profile:
@@ -193,18 +209,22 @@ class SlabRenderer:
             # a covered metavoxel costs its voxels' loop overhead even with few particles: ~2 pairs' worth (measured shape)
             wd = pairs.astype(np.float64) + 2.0 * covered.astype(np.float64) + 1e-9
             wm = samples.astype(np.float64) + 1e-9
-        mine = (self.z0, self.z1, density_ms, march_ms, wd[self.z0:self.z1].tolist(), wm[self.z0:self.z1].tolist())
+        # the sweep moves 16 bytes per voxel of a covered metavoxel; ~0.6 of the HBM rate measured alone
+        gx, gy, _ = e.grid
+        sweep = np.full(nz, gx * gy * float(e.N) ** 3 * 16.0 / 4.0e12 * 1e3)
+        if self.head_fused:   # rank 0 timed the fused kernel: take the sweep's share out, the model adds it back
+            density_ms = max(0.1 * density_ms, density_ms - HEAD_FUSED_SWEEP_FACTOR * float(sweep[self.z0:self.z1].sum()))
+        mine = (self.z0, self.z1, density_ms, march_ms, wd[self.z0:self.z1].tolist(), wm[self.z0:self.z1].tolist(), self.head_fused)
         rows = [None] * self.world
         d.all_gather_object(rows, mine)
+        fused0 = bool(rows[0][6])
+        rows = [r[:6] for r in rows]
         dc, mc = np.zeros(nz), np.zeros(nz)
         for (a, b, dm, mm, w1, w2) in rows:
             w1, w2 = np.asarray(w1), np.asarray(w2)
             dc[a:b] = dm * w1 / w1.sum()
             mc[a:b] = mm * w2 / w2.sum()
-        # the sweep moves 16 bytes per voxel of a covered metavoxel; ~0.6 of the HBM rate measured alone
-        gx, gy, _ = e.grid
-        sweep = np.full(nz, gx * gy * float(e.N) ** 3 * 16.0 / 4.0e12 * 1e3)
-        slabs_, _ = balance_slabs(dc, sweep, mc, self.world)
+        slabs_, _ = balance_slabs(dc, sweep, mc, self.world, head_sweep_factor=HEAD_FUSED_SWEEP_FACTOR if fused0 else 1.0)
         self.set_slab(*slabs_[self.rank])
         self._times = None
         return slabs_
@@ -385,6 +405,9 @@ class CudaSlabEngine:
 
     def fill_sweep_linked(self):
         self.eng.fill_sweep_linked()
+
+    def fill_linked(self):
+        self.eng.fill_linked()
 
     def image_link_neighbours(self, dist, rank, world, w, h):
         """Exchange the IPC handles of the image receive buffers and map every rank's buffer (same node only)."""
