@@ -62,6 +62,62 @@ class Twin:
         self.cube = cubemap_r8.astype(np.float64) / 255.0
         self.E = cubemap_r8.shape[1]
         self.lists = None
+        self.depth_map = None                                                # lightDepthMap (VPR.cs:274), None = cleared to 1
+
+    # VPR.cs:320-367 InitCameraAtLight / UpdatePositionOfCameraAtLight: orthographic, at centre - forward * 200
+    def light_camera_to_world(self):
+        return trs(self.center - self.f * 200.0, self.lq, 1.0)
+
+    # VPR.cs:184 + GenerateLightDepthMap.shader:6-31 (Cull Front, ZWrite On, ZTest Less, depth only)
+    def rasterize_depth(self, tris, near=0.3, far=1000.0, edge_eps=1e-4):
+        """Depth map [NY*N][NX*N] of the occluders seen from the light, and a mask of pixels whose centre lies within
+        edge_eps (barycentric) of a drawn triangle's edge: there the fill rule decides, which this restatement does not
+        model (the oracle uses D3D's top-left rule).  Barycentrics come from a 2x2 solve per triangle, not from edge
+        functions; double precision."""
+        W, H = int(self.G[0]) * self.N, int(self.G[1]) * self.N
+        r, t = self.G[0] * self.s * 0.5, self.G[1] * self.s * 0.5                 # VPR.cs:340 orthographic extents
+        w2lc = np.linalg.inv(self.light_camera_to_world())
+        depth = np.ones((H, W))
+        edge = np.zeros((H, W), dtype=bool)
+        for tri in np.asarray(tris, dtype=np.float64):
+            p = xf(w2lc, tri)
+            sx = (p[:, 0] / r * 0.5 + 0.5) * W
+            sy = (p[:, 1] / t * 0.5 + 0.5) * H
+            sz = (p[:, 2] - near) / (far - near)
+            m = np.array([[sx[1] - sx[0], sx[2] - sx[0]], [sy[1] - sy[0], sy[2] - sy[0]]])
+            det = np.linalg.det(m)
+            if not det > 0:                                                      # clockwise from the light = front face: culled
+                continue
+            x0, x1 = max(0, int(np.floor(sx.min() - 0.5))), min(W - 1, int(np.ceil(sx.max() - 0.5)))
+            y0, y1 = max(0, int(np.floor(sy.min() - 0.5))), min(H - 1, int(np.ceil(sy.max() - 0.5)))
+            if x1 < x0 or y1 < y0:
+                continue
+            gx, gy = np.meshgrid(np.arange(x0, x1 + 1) + 0.5, np.arange(y0, y1 + 1) + 0.5)
+            bc = np.linalg.solve(m, np.stack([gx.ravel() - sx[0], gy.ravel() - sy[0]]))
+            l1, l2 = bc[0].reshape(gx.shape), bc[1].reshape(gx.shape)
+            l0 = 1 - l1 - l2
+            lmin = np.minimum(l0, np.minimum(l1, l2))
+            z = l0 * sz[0] + l1 * sz[1] + l2 * sz[2]
+            inside = (lmin >= 0) & (z >= 0) & (z <= 1)
+            sub = depth[y0:y1 + 1, x0:x1 + 1]
+            sub[...] = np.where(inside & (z < sub), z, sub)
+            edge[y0:y1 + 1, x0:x1 + 1] |= np.abs(lmin) < edge_eps
+        return depth, edge
+
+    # tex2D(_LightDepthMap, uv): bilinear, clamp (Fill.shader:216)
+    def sample_depth(self, u, v):
+        if self.depth_map is None:
+            return np.ones_like(u)
+        H, W = self.depth_map.shape
+        fx, fy = u * W - 0.5, v * H - 0.5
+        x0, y0 = np.floor(fx), np.floor(fy)
+        wx, wy = fx - x0, fy - y0
+        x0, y0 = x0.astype(np.int64), y0.astype(np.int64)
+        cx, cy = (lambda a: np.clip(a, 0, W - 1)), (lambda a: np.clip(a, 0, H - 1))
+        d = self.depth_map
+        top = d[cy(y0), cx(x0)] * (1 - wx) + d[cy(y0), cx(x0 + 1)] * wx
+        bot = d[cy(y0 + 1), cx(x0)] * (1 - wx) + d[cy(y0 + 1), cx(x0 + 1)] * wx
+        return top * (1 - wy) + bot * wy
 
     # A.1  VPR.cs:370-394
     def mv_center(self, x, y, z):
@@ -155,11 +211,17 @@ class Twin:
         ao = np.zeros((N, N, N))
         ds, of = float(np.float32(sc["displacementScale"])), float(np.float32(sc["opacityFactor"]))
         near_surface = np.zeros((N, N, N), dtype=bool)
+        count = np.zeros((N, N, N), dtype=np.int64)                          # particles that contain the voxel
         for n_i, pi in enumerate(plist):
             q = xf(self.W2P[pi], vox)
             qq = (q * q).sum(-1)
             inside = qq <= 0.25
             near_surface |= np.abs(qq - 0.25) < 1e-5
+            # texCUBE filters each face on its own (clamp): a direction whose two largest components tie sits on a face seam,
+            # where fp32 and fp64 may pick different faces - a discontinuity like the sphere surface
+            srt = np.sort(np.abs(q), axis=-1)
+            near_surface |= inside & (srt[..., 1] > srt[..., 2] * (1 - 1e-4))
+            count += inside
             raw = self.sample_cube(2 * q)
             nd = ds * raw + (1 - ds)
             d2 = 4 * qq
@@ -169,11 +231,16 @@ class Twin:
                 dens = dens * self.opacity[pi]
             density += np.where(inside, dens, 0.0)
             ao = np.where(inside, nd if n_i == 0 else np.maximum(ao, nd), ao)
-        # occlusion: no occluders in the synthetic scenes -> depth map == 1 -> far plane
-        lc = trs(self.center - self.f * 200.0, self.lq, 1.0)
-        z0 = xf(np.linalg.inv(lc), vox0)[..., 2]
-        depth = 1.0 * (1000.0 - 0.3) + 0.3
-        shadow = np.trunc((depth - z0) / (self.sb / N))
+        # occlusion, Fill.shader:211-221: the scene's depth seen from the light at this voxel column (cleared map = far plane)
+        z0 = xf(np.linalg.inv(self.light_camera_to_world()), vox0)[..., 2]
+        px = np.arange(N) + 0.5
+        uu = np.broadcast_to((px[None, :] + x * N) / (self.G[0] * N), (N, N))
+        vv = np.broadcast_to((px[:, None] + y * N) / (self.G[1] * N), (N, N))
+        depth = self.sample_depth(uu, vv) * (1000.0 - 0.3) + 0.3
+        fsi = (depth - z0) / (self.sb / N)
+        shadow = np.trunc(fsi)
+        self.last_shadow_margin = np.abs(fsi - np.rint(fsi))                  # columns whose shadow index sits on an integer
+        self.last_shadow = shadow                                             # first slice in shadow, per voxel column
         T = np.ones((N, N)) if z == 0 else sheet_in.astype(np.float64).copy()
         prop = T.copy()
         amb = np.asarray(sc["ambient"], dtype=np.float32).astype(np.float64)
@@ -186,6 +253,7 @@ class Twin:
             out[kk, ..., 0:3] = 0.4 * T[..., None] + amb * ao[kk][..., None]
             out[kk, ..., 3] = density[kk]
             T = T * (1 / (1 + density[kk]))
+        self.last_inside_count = count
         return out, prop, near_surface
 
     # A.7  VPR.cs:613-711: metavoxels in submission order with their blend mode
