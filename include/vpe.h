@@ -281,6 +281,11 @@ int vpe_march_footprint(VpeContext* ctx, const VpeCamera* cam, int64_t* uniqueTe
 /* brick (x,y,z) as N*N*N half4 in [slice][row][col] order (≙ mvFillTextures[z,y,x], VPR.cs:312);
  * returns 1 in *covered if the metavoxel has particles (VPR.cs:511), else 0 and no data. */
 int vpe_read_brick(VpeContext* ctx, int x, int y, int z, uint16_t* half4, int* covered);
+/* The march's empty-space bitmap of metavoxel (x,y,z) (CUDA library only; the reference has no such structure):
+ * words [z0][y0][ceil(N/32)], bit x0 set iff one of the 8 texels of the trilinear footprint based at (x0,y0,z0) -
+ * texels x0..x0+1, y0..y0+1, z0..z0+1 inside the brick - has a non-zero stored density. The tests compare it with
+ * the brick itself: a bit that is wrongly clear would change the image, one that is wrongly set only costs time. */
+int vpe_read_sample_bitmap(VpeContext* ctx, int x, int y, int z, uint32_t* words, int* covered);
 /* light sheet (≙ lightPropogationUAV, VPR.cs:266): (NY*N) rows x (NX*N) floats. */
 int vpe_read_light_sheet(VpeContext* ctx, float* sheet);
 /* particle indices binned to metavoxel (x,y,z), in list order; returns count in *n (cap = size

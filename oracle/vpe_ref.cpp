@@ -1174,6 +1174,7 @@ int vpe_sheet_link_create(VpeContext* c, void*, void**) { return fail(c, VPE_E_U
 int vpe_sheet_link_connect(VpeContext* c, const void*, const void*, int) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
 int vpe_fill_sweep_linked(VpeContext* c) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
 int vpe_fill_linked(VpeContext* c) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
+int vpe_read_sample_bitmap(VpeContext* c, int, int, int, uint32_t*, int*) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
 int vpe_sheet_link_status(VpeContext* c, int*) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
 int vpe_march_partial_device(VpeContext* c, const VpeCamera*, float*, float*, int32_t*) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }
 int vpe_image_link_create(VpeContext* c, int, int, int, int, void*, void**) { return fail(c, VPE_E_UNSUPPORTED, "oracle"); }

@@ -108,6 +108,7 @@ PROTOTYPES = {
     "vpe_sheet_link_connect": (C.c_int, [_P, _P, _P, C.c_int]),
     "vpe_fill_sweep_linked": (C.c_int, [_P]),
     "vpe_fill_linked": (C.c_int, [_P]),
+    "vpe_read_sample_bitmap": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
     "vpe_sheet_link_status": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "vpe_march_partial_device": (C.c_int, [_P, C.POINTER(VpeCamera), _P, _P, _P]),
     "vpe_image_link_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.POINTER(_P)]),

@@ -90,7 +90,8 @@ struct VpeContext {
     DevBuf<float> dCube, dDepth, dSheet;
     DevBuf<float4> dCubeFp;          // bilinear footprints of the cubemap, [6][E+1][E+1]
     DevBuf<uint2> dBricks;
-    DevBuf<unsigned> dNz, dOcc;      // per brick [z][y] rows of occRowWords words, bit x: non-zero density / occupied sample base (k_occ_build)
+    DevBuf<unsigned> dNz, dOcc;      // dNz: per brick [warp tile][z] words, non-zero density bits of the fill's 8x4 tiles; dOcc: per brick [z][y] rows of
+                                     // occRowWords words, bit x: occupied sample base (k_occ_build)
     int occRowWords = 0;             // ceil(N / 32)
     VpeDebugOptions dbg;             // vpe_set_debug_options (all zero = production behaviour)
     DevBuf<float4> dMvCam;
@@ -388,11 +389,9 @@ int fill_prepare_impl(VpeContext* c, const float* particlesDev, int n, const Vpe
     {
         // empty-space bitmaps: every word of a covered brick is rewritten by each fill (k_fill_columns / k_occ_build)
         const size_t words = std::max<size_t>(1, (size_t)c->nCovered * g.N * g.N * c->occRowWords);
-        if (words > c->dNz.cap) {
-            CUDA_TRY(c, c->dNz.ensure(words + words / 16));
-            CUDA_TRY(c, c->dOcc.ensure(words + words / 16));
-            CUDA_TRY(c, cudaMemsetAsync(c->dNz.p, 0, c->dNz.cap * sizeof(unsigned), c->stream));  // the pad bytes of short rows
-        }
+        const size_t nzWords = std::max<size_t>(1, (size_t)c->nCovered * ((g.N + 7) / 8) * ((g.N + 3) / 4) * g.N);  // [brick][warp tile][z]
+        if (words > c->dOcc.cap) CUDA_TRY(c, c->dOcc.ensure(words + words / 16));
+        if (nzWords > c->dNz.cap) CUDA_TRY(c, c->dNz.ensure(nzWords + nzWords / 16));
     }
     // VPR.cs:498-499: clear the light propagation texture to 1
     const size_t sheetN = (size_t)g.NX * g.N * g.NY * g.N;
@@ -479,7 +478,7 @@ int fill_region_impl(VpeContext* c, int x0, int x1, int y0, int y1, FillPhase ph
     a.covered = c->dCovered.p; a.sliceStart = c->dSliceStart.p; a.cellStart = c->dCellStart.p; a.pairs = c->dPairs.p;
     a.pfill = c->dPfill.p; a.cube = c->dCube.p; a.depth = c->depthSet ? c->dDepth.p : nullptr;
     a.sheet = c->dSheet.p; a.bricks = c->dBricks.p;
-    a.nz = reinterpret_cast<unsigned char*>(c->dNz.p); a.nzRowBytes = c->occRowWords * 4;
+    a.nz = c->dNz.p;
     a.x0 = x0; a.x1 = x1; a.y0 = y0; a.y1 = y1;
     a.densityDone = nullptr; a.densityEpoch = 0;
     const bool wholeGrid = x0 == 0 && y0 == 0 && x1 == g.NX && y1 == g.NY;
@@ -1474,6 +1473,22 @@ int vpe_read_brick(VpeContext* c, int x, int y, int z, uint16_t* half4, int* cov
             }
         }
     }
+    return VPE_OK;
+}
+
+int vpe_read_sample_bitmap(VpeContext* c, int x, int y, int z, uint32_t* words, int* covered) {
+    if (!c || !covered) return VPE_E_INVALID_ARG;
+    if (x < 0 || y < 0 || z < 0 || x >= c->g.NX || y >= c->g.NY || z >= c->g.NZ) return fail(c, VPE_E_INVALID_ARG, "metavoxel index out of range");
+    DeviceScope deviceScope(c->device);
+    *covered = 0;
+    if (!c->filledOnce || !c->dOcc.p) return VPE_OK;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    int flat = (z * c->g.NY + y) * c->g.NX + x, brick = -1;
+    CUDA_TRY(c, cudaMemcpy(&brick, c->dBrickOf.p + flat, sizeof(int), cudaMemcpyDeviceToHost));
+    if (brick < 0) return VPE_OK;
+    *covered = 1;
+    const size_t n = (size_t)c->g.N * c->g.N * c->occRowWords;
+    if (words) CUDA_TRY(c, cudaMemcpy(words, c->dOcc.p + (size_t)brick * n, n * sizeof(unsigned), cudaMemcpyDeviceToHost));
     return VPE_OK;
 }
 

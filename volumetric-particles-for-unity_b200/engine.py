@@ -364,6 +364,17 @@ class Engine:
         return n.value
 
     # -- test hooks -----------------------------------------------------------------------
+    def read_sample_bitmap(self, x, y, z):
+        """The march's empty-space bitmap of a metavoxel as bool [z0][y0][x0] (None when not covered)."""
+        rw = (self.N + 31) // 32
+        words = np.empty((self.N, self.N, rw), dtype=np.uint32)
+        covered = C.c_int(0)
+        self._check(self.lib.vpe_read_sample_bitmap(self._ctx, x, y, z, words.ctypes.data, C.byref(covered)))
+        if not covered.value:
+            return None
+        bits = (words[..., None] >> np.arange(32, dtype=np.uint32)) & 1
+        return bits.reshape(self.N, self.N, rw * 32)[..., :self.N].astype(bool)
+
     def read_brick(self, x, y, z):
         """half4 brick as uint16 [N][N][N][4] (slice, row, col, rgba) or None when not covered."""
         out = np.empty((self.N, self.N, self.N, 4), dtype=np.uint16)
