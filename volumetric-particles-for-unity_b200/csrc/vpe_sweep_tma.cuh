@@ -129,8 +129,7 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, GridParams g, FillArgs a, 
                 propagated = transmitted;
                 if (GRAY) {  // slice 0 is not in the (shifted) boxes: every thread sweeps its own texel of it from global memory
                     const uint2 t = __ldcg(a.bricks + (size_t)itc.entry * NN * N + (size_t)py * g.rowStride + px);
-                    const uint2 o = sweep_voxel(g, 0, shadowIndex, borderVoxelIndex, __uint_as_float(t.x), __uint_as_float(t.y), transmitted, propagated);
-                    prevWord = __byte_perm(o.x, o.y, 0x7610);
+                    prevWord = sweep_voxel_gray(g, 0, shadowIndex, borderVoxelIndex, __uint_as_float(t.x), __uint_as_float(t.y), transmitted, propagated);
                 }
             }
             mbar_wait(&full[s], (G / STAGES) & 1u);
@@ -146,10 +145,8 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, GridParams g, FillArgs a, 
                 const uint2 t = sb[j * SLICE_TEXELS];
                 if (GRAY) {
                     unsigned word = 0u;
-                    if (slice < N) {
-                        const uint2 o = sweep_voxel(g, slice, shadowIndex, borderVoxelIndex, __uint_as_float(t.x), __uint_as_float(t.y), transmitted, propagated);
-                        word = __byte_perm(o.x, o.y, 0x7610);
-                    }
+                    if (slice < N)
+                        word = sweep_voxel_gray(g, slice, shadowIndex, borderVoxelIndex, __uint_as_float(t.x), __uint_as_float(t.y), transmitted, propagated);
                     sb[j * SLICE_TEXELS] = make_uint2(prevWord, word);
                     prevWord = word;
                 } else {
