@@ -50,8 +50,8 @@ def image_band(height, world, rank):
     return min(rank * per, height), min((rank + 1) * per, height)
 
 
-# Cost of the sweep inside the fused fill kernel relative to the sweep as a kernel of its own (cfg3, one B200: fused 10.3 ms,
-# density pass 9.2 ms, sweep alone 3.1 ms): what the rank at the head of the chain pays for its sweep (profiles/r02_scaling.md).
+# Cost of the sweep inside the fused fill kernel relative to the sweep as a kernel of its own (cfg3, one B200: fused 9.24 ms,
+# density pass 8.21 ms, sweep alone 3.09 ms): what the rank at the head of the chain pays for its sweep (profiles/r02_scaling.md).
 HEAD_FUSED_SWEEP_FACTOR = 0.35
 
 
