@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VPE_ABI_VERSION 1
+#define VPE_ABI_VERSION 2   /* 2: VpeStats.raySamplesSkipped, VpeDebugOptions, vpe_fill_linked, slice profile / bitmap / division hooks */
 
 enum {
     VPE_OK = 0,

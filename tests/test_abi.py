@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(which):
     for name in declared_functions():
         assert hasattr(lib, name), "%s does not export %s" % (which, name)
     _abi.bind(lib)
-    assert lib.vpe_abi_version() == 1
+    assert lib.vpe_abi_version() == _abi.ABI_VERSION == 2
     assert lib.vpe_backend() == (b"cuda" if which == "cuda" else b"oracle")
     cfg = _abi.VpeConfig()
     lib.vpe_default_config(C.byref(cfg))  # the demo scene's inspector values (scene:9013-9026)

@@ -74,6 +74,8 @@ class VpeDebugOptions(C.Structure):
                 ("sweepOverlap", C.c_int32), ("noTmaSweep", C.c_int32), ("profileSlices", C.c_int32), ("noHeadFused", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
+ABI_VERSION = 2   # VPE_ABI_VERSION of include/vpe.h this mirror was written against
+
 assert C.sizeof(VpeParticle) == 28
 
 _P = C.c_void_p

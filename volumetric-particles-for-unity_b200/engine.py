@@ -35,7 +35,7 @@ def load_cuda_library():
         _abi.bind(lib)
         if lib.vpe_backend() != b"cuda":
             raise RuntimeError("libvpe_cuda.so reports backend %r" % lib.vpe_backend())
-        if lib.vpe_abi_version() != 1:
+        if lib.vpe_abi_version() != _abi.ABI_VERSION:
             raise RuntimeError("ABI version mismatch")
         _cuda_lib = lib
     return _cuda_lib
